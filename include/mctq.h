@@ -1,0 +1,187 @@
+/*
+ * mctq.h -- C ABI of libmctq_sm100.so, the B200 (sm_100a) fake-quant path that replaces the arithmetic
+ * underneath mct_quantizers' PyTorch inferable quantizers.
+ *
+ * The reference (sony/mct_quantizers 1.6.0) is pure Python and has no FFI of its own: its hot path is
+ *   - torch.fake_quantize_per_tensor_affine / torch.fake_quantize_per_channel_affine, called from
+ *       mct_quantizers/pytorch/quantizers/weights_inferable_quantizers/weights_symmetric_inferable_quantizer.py:139-151
+ *       mct_quantizers/pytorch/quantizers/weights_inferable_quantizers/weights_uniform_inferable_quantizer.py:153-165
+ *       mct_quantizers/pytorch/quantizers/activation_inferable_quantizers/activation_symmetric_inferable_quantizer.py:113-117
+ *       mct_quantizers/pytorch/quantizers/activation_inferable_quantizers/activation_uniform_inferable_quantizer.py:124-128
+ *   - lut_quantizer / int_quantization_with_threshold, mct_quantizers/pytorch/quantizer_utils.py:95-170, called from
+ *       .../weights_lut_symmetric_inferable_quantizer.py:114-122 and .../activation_lut_pot_inferable_quantizer.py:86-91
+ * Each entry point below names the reference call site(s) it stands in for.  INTEGRATION.md shows the
+ * ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a positive cudaError_t on a CUDA failure, or a negative
+ *     MCTQ_E_* code on a bad argument; nothing throws, nothing allocates device memory, and the
+ *     device-pointer entry points never synchronise: work is enqueued on `stream` (a cudaStream_t
+ *     passed as void*; NULL = legacy default stream).
+ *   - tensors are contiguous and are viewed as [outer][C][inner]; element i of the logical tensor has
+ *     channel (i / inner) % C.  C == 1 is per-tensor quantisation.  `elem_offset` is the logical index
+ *     of x[0], so a caller can hand in any flat slice of a tensor (batch / channel-block shards,
+ *     host-staging chunks) without re-deriving parameters.
+ *   - dtype tags: MCTQ_F32 / MCTQ_BF16 / MCTQ_F16 describe x (and y for the affine ops).
+ *   - arithmetic contract (bit-exact with CPU torch 2.11):
+ *       affine:  inv = 1.0f / s;  q = clamp(rint(x * inv) + zp, qmin, qmax);  y = (q - zp) * s
+ *       lut:     t = clip((x / (thr + eps)) * 2^(bw - signed), lo, hi);  idx = first argmin_k |t - lut_k|;
+ *                y = (lut[idx] / 2^(bw - signed)) * thr            (y is always f32)
+ *     valid for finite inputs, |qmin - zp|, |qmax - zp| < 2^21 (else an rint-based slower variant is
+ *     selected automatically) and NaN -> qmin / LUT index 0.
+ */
+#ifndef MCTQ_H_
+#define MCTQ_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCTQ_ABI_VERSION 1
+
+/* dtype tags */
+#define MCTQ_F32 0
+#define MCTQ_BF16 1
+#define MCTQ_F16 2
+
+/* integer-code / LUT-index emission */
+#define MCTQ_CODES_NONE 0
+#define MCTQ_CODES_INT8 1 /* one byte per element: (uint8_t)(q & 0xff) -- int8 when qmin < 0, uint8 otherwise */
+#define MCTQ_CODES_INT4 2 /* two elements per byte, element 2j in the low nibble; n is rounded up to even */
+
+/* argument errors (negative so they cannot collide with cudaError_t) */
+#define MCTQ_E_BADARG (-1)
+#define MCTQ_E_DTYPE (-2)
+#define MCTQ_E_RANGE (-3)   /* qmin > qmax, or codes requested for a range that does not fit the code width */
+#define MCTQ_E_LUT (-4)     /* malformed LUT table blob */
+#define MCTQ_E_NODEVICE (-5)
+
+int mctq_abi_version(void);
+/* compile-time facts a caller can assert on: "sm_100a", tile geometry, ... (static string, never freed) */
+const char* mctq_build_info(void);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Affine fake-quant, device pointers.
+ * Replaces: torch.fake_quantize_per_channel_affine(x, scales, zero_points, axis, qmin, qmax)
+ *             (weights_symmetric_inferable_quantizer.py:139-144, weights_uniform_inferable_quantizer.py:153-158)
+ *           torch.fake_quantize_per_tensor_affine(x, scales[1], zero_points[1], qmin, qmax)   [tensor qparams]
+ *             (weights_symmetric_inferable_quantizer.py:147-151, weights_uniform_inferable_quantizer.py:160-165)
+ * x, y       device, n elements of x_dtype; y may be NULL when only codes are wanted
+ * codes      device or NULL; layout per code_mode
+ * scale, zp  device arrays of C entries (read on the device: no host sync, unlike the reference's
+ *            per-channel path which does two .item() round trips per call)
+ */
+int mctq_fq_affine(const void* x, void* y, void* codes, int64_t n, int x_dtype,
+                   const float* scale, const int32_t* zp, int64_t C, int64_t inner, int64_t elem_offset,
+                   int32_t qmin, int32_t qmax, int code_mode, void* stream);
+
+/* Per-tensor affine fake-quant with scalar parameters passed by value.
+ * Replaces: torch.fake_quantize_per_tensor_affine(x, scale=float, zero_point=int, qmin, qmax)
+ *             (activation_symmetric_inferable_quantizer.py:113-117, activation_uniform_inferable_quantizer.py:124-128)
+ * `scale` is the Python float already narrowed to f32 (what ATen does internally). */
+int mctq_fq_affine_scalar(const void* x, void* y, void* codes, int64_t n, int x_dtype,
+                          float scale, int32_t zp, int32_t qmin, int32_t qmax, int code_mode, void* stream);
+
+/* Dequantise codes written by the functions above: y = (q - zp) * s  (f32 out).  No reference call site:
+ * this is the consumer side of the code wire format. */
+int mctq_dequant_affine(const void* codes, int code_mode, int is_signed, float* y, int64_t n,
+                        const float* scale, const int32_t* zp, int64_t C, int64_t inner, int64_t elem_offset,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Whole-model weight quantisation: one launch over a table of tensors.
+ * Replaces the per-layer loop  for name, w, quantizer in self._weights_vars: quantizer(w)
+ *   (mct_quantizers/pytorch/quantize_wrapper.py:228-240 and :260-270) for affine weight quantizers.
+ * `descs` and `tile_starts` live in DEVICE memory (the caller uploads them once; weights do not move).
+ * tile_starts has n_desc + 1 entries: tile_starts[k] = first tile of tensor k, in units of
+ * mctq_multi_tile_elems(dtype) elements; mctq_multi_plan fills it on the host.
+ */
+typedef struct MctqTensorDesc {
+    const void* x;
+    void* y;
+    void* codes; /* or NULL */
+    const float* scale;
+    const int32_t* zp;
+    int64_t n;
+    int64_t C;
+    int64_t inner;
+    int32_t qmin;
+    int32_t qmax;
+    int32_t dtype;
+    int32_t code_mode;
+} MctqTensorDesc;
+
+int64_t mctq_multi_tile_elems(void);
+/* host helper: fills tile_starts[0..n_desc] from descs[k].n (both HOST arrays); returns total tiles or <0 */
+int64_t mctq_multi_plan(const MctqTensorDesc* descs_host, int n_desc, int32_t* tile_starts_host);
+int mctq_fq_affine_multi(const MctqTensorDesc* descs_dev, const int32_t* tile_starts_dev, int n_desc,
+                         int64_t total_tiles, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * LUT (nearest-centroid) fake-quant.
+ * Replaces: lut_quantizer(...)  mct_quantizers/pytorch/quantizer_utils.py:95-139 (which calls
+ *           int_quantization_with_threshold :142-170) as used by
+ *           weights_lut_symmetric_inferable_quantizer.py:114-122, weights_lut_pot_inferable_quantizer.py:74-104,
+ *           activation_lut_pot_inferable_quantizer.py:86-91.
+ *
+ * The centroid list is first compiled (on the host, once per quantizer) into a search table: sorted
+ * unique centroids, the exact f32 decision threshold between each adjacent pair under torch.argmin's
+ * first-minimum rule, and the original index of every sorted entry.  The table is a POD blob of
+ * mctq_lut_table_bytes(K) bytes that the caller copies to the device; K (the length of the original
+ * centroid list, <= 256) travels with it because the blob's geometry is a function of K alone.
+ */
+size_t mctq_lut_table_bytes(int K);
+int mctq_lut_build_table(const float* lut_host, int K, int lut_values_bitwidth, int is_signed,
+                         void* table_host_out, size_t table_bytes);
+
+/* weights flavour: thr is a DEVICE f32 array [C]; d_c = thr_c + (float)eps (f32 add), no intermediate
+ * rounding, f32 output.  idx (optional) receives the LUT index per element (MCTQ_CODES_INT8: one byte,
+ * MCTQ_CODES_INT4: packed nibbles, K <= 16). */
+int mctq_fq_lut(const void* x, float* y, void* idx, int64_t n, int x_dtype,
+                const void* table_dev, int K, const float* thr, int64_t C, int64_t inner, int64_t elem_offset,
+                float eps, int idx_mode, void* stream);
+
+/* activation flavour: threshold and eps are Python floats in the reference, so the divisor is
+ * d = (float)(thr + eps) computed in double by the caller and passed by value with thr_f32 = (float)thr;
+ * for bf16/f16 inputs the reference's eager ops round the normalised value back to the input dtype
+ * before the search (round_to_x_dtype = 1). */
+int mctq_fq_lut_scalar(const void* x, float* y, void* idx, int64_t n, int x_dtype,
+                       const void* table_dev, int K, float divisor, float thr_f32, int round_to_x_dtype,
+                       int idx_mode, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Host-buffer entry points: the same operators for tensors that live in HOST memory (pinned memory
+ * overlaps; pageable memory works but serialises).  The data is streamed through `staging_dev`
+ * (device scratch owned by the caller, >= mctq_host_staging_min_bytes()) in chunks on internal streams:
+ * H2D copy, kernel and D2H copy of neighbouring chunks overlap.  Parameters are HOST arrays.  These
+ * calls return after y_host is complete (they synchronise their internal streams only).
+ * They are what a CPU-tensor call of a quantizer maps to: the product has no CPU arithmetic path.
+ */
+size_t mctq_host_staging_min_bytes(void);
+int mctq_fq_affine_host(const void* x_host, void* y_host, int64_t n, int x_dtype,
+                        const float* scale_host, const int32_t* zp_host, int64_t C, int64_t inner,
+                        int32_t qmin, int32_t qmax, void* staging_dev, size_t staging_bytes, int device);
+int mctq_fq_lut_host(const void* x_host, float* y_host, int64_t n, int x_dtype,
+                     const void* table_host, int K, const float* thr_host, int64_t C, int64_t inner,
+                     float eps, int scalar_mode, float divisor, float thr_f32, int round_to_x_dtype,
+                     void* staging_dev, size_t staging_bytes, int device);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Introspection / test hooks (no reference counterpart).
+ */
+/* launches of this library's kernels since load (what bench.py reports as gpu_launches) */
+int64_t mctq_launch_count(void);
+/* variant selection for experiments: key 0 = unroll (2,4,8), key 1 = force rint path (0/1),
+ * key 2 = force IEEE-division LUT path (0/1); returns previous value or <0 */
+int mctq_set_tuning(int key, int value);
+/* device self-test of the 5-op correctly-rounded division used by the LUT kernels against __fdiv_rn
+ * on n_pairs pseudo-random (x, d) pairs; *mismatches_dev (device int64) receives the number that differ */
+int mctq_selftest_division(int64_t n_pairs, uint64_t seed, int64_t* mismatches_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCTQ_H_ */

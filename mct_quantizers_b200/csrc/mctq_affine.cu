@@ -1,0 +1,438 @@
+// mctq_affine.cu -- affine (round-clip-dequant) fake-quant kernels and their C ABI entry points.
+#include "mctq_common.cuh"
+
+namespace mctq {
+
+constexpr float kMagic = 12582912.0f;      // 1.5 * 2^23: (t + kMagic) - kMagic == rint(t) for |t| < 2^22
+constexpr int32_t kFastRangeLimit = 1 << 21;
+
+struct AffineArgs {
+    const void* x;
+    void* y;
+    void* codes;
+    int64_t n;
+    const float* scale;     // device [C] or NULL (then scale_val / zp_val)
+    const int32_t* zp;
+    float scale_val;
+    int32_t zp_val;
+    int64_t C, inner, elem_offset;
+    int32_t qmin, qmax;
+    // channel-window geometry (host-derived)
+    FastDiv div_inner, div_W;
+    uint32_t W;             // staged channel slots
+    uint32_t bigrow;        // inner >= tile elems: a tile touches at most two rows
+};
+
+template <bool RINT> struct AffineOp {
+    using Args = AffineArgs;
+    struct ChanParams { float inv, s, lo, hi; int zp; };
+    static constexpr int kSmemFloatsPerChan = 3;
+
+    __device__ static __forceinline__ ChanParams make(float s, int zp, const Args& a) {
+        ChanParams p;
+        p.s = s;
+        p.inv = __fdiv_rn(1.0f, s);                  // IEEE reciprocal of the f32 scale (ATen: 1.0f / scale)
+        p.zp = zp;
+        if (RINT) { p.lo = (float)a.qmin; p.hi = (float)a.qmax; }
+        else { p.lo = (float)(a.qmin - zp); p.hi = (float)(a.qmax - zp); }
+        return p;
+    }
+    __device__ static __forceinline__ ChanParams uniform(const Args& a) {
+        float s = a.scale ? __ldg(a.scale) : a.scale_val;
+        int zp = a.zp ? __ldg(a.zp) : a.zp_val;
+        return make(s, zp, a);
+    }
+    __device__ static __forceinline__ void stage(float* sm, uint32_t W, uint32_t slot, int64_t c, const Args& a) {
+        ChanParams p = make(__ldg(a.scale + c), __ldg(a.zp + c), a);
+        sm[slot] = p.inv;
+        sm[W + slot] = p.s;
+        sm[2 * W + slot] = __int_as_float(p.zp);
+    }
+    __device__ static __forceinline__ ChanParams fetch(const float* sm, uint32_t W, uint32_t slot, const Args& a) {
+        ChanParams p;
+        p.inv = sm[slot];
+        p.s = sm[W + slot];
+        p.zp = __float_as_int(sm[2 * W + slot]);
+        if (RINT) { p.lo = (float)a.qmin; p.hi = (float)a.qmax; }
+        else { p.lo = (float)(a.qmin - p.zp); p.hi = (float)(a.qmax - p.zp); }
+        return p;
+    }
+    // returns y; code receives the clamped integer q
+    template <bool WANT_CODE>
+    __device__ static __forceinline__ float apply(float x, const ChanParams& p, int& code) {
+        float t = __fmul_rn(x, p.inv);
+        if (!RINT) {
+            // (t + M) - M rounds half-to-even exactly for |t| < 2^22 and stays out of [lo, hi] beyond it;
+            // anything that rounds to zero comes out as +0.0, so y never carries the sign of a tiny negative
+            // input (ATen subtracts the integer zero point, which has the same effect).  Clamping
+            // r to [qmin - zp, qmax - zp] equals clamp(r + zp, qmin, qmax) - zp on integer-valued floats.
+            float r = __fsub_rn(__fadd_rn(t, kMagic), kMagic);
+            float c = fminf(fmaxf(r, p.lo), p.hi);           // fmaxf(NaN, lo) = lo: NaN -> qmin
+            if (WANT_CODE) code = (int)c + p.zp;
+            return __fmul_rn(c, p.s);
+        } else {
+            float zf = (float)p.zp;
+            float q = __fadd_rn(rintf(t), zf);
+            q = fminf(fmaxf(q, p.lo), p.hi);
+            if (WANT_CODE) code = (int)q;
+            return __fmul_rn(__fsub_rn(q, zf), p.s);
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------ affine kernel
+template <typename T, int CHMODE, int CODE, int UNROLL, bool RINT>
+__global__ void __launch_bounds__(kThreads) fq_affine_kernel(const AffineArgs a) {
+    using Op = AffineOp<RINT>;
+    constexpr int V = 16 / sizeof(T);
+    constexpr int WORDS = 4;
+    constexpr uint32_t TILE = kThreads * UNROLL * V;
+    extern __shared__ float sm_par[];
+    __shared__ Window sm_win;
+
+    const uint32_t tid = threadIdx.x;
+    const int64_t t0 = (int64_t)blockIdx.x * TILE;
+    const int64_t remaining = a.n - t0;
+    const bool full = remaining >= (int64_t)TILE;
+    const T* xt = reinterpret_cast<const T*>(a.x) + t0;
+
+    uint32_t w[UNROLL][WORDS];
+    if (full) {
+#pragma unroll
+        for (int j = 0; j < UNROLL; ++j) ld_words<WORDS>(xt + (size_t)(j * kThreads + tid) * V, w[j]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < UNROLL; ++j) {
+            int64_t l = (int64_t)(j * kThreads + tid) * V;
+            if (l + V <= remaining) ld_words<WORDS>(xt + l, w[j]);
+            else {
+                T tmp[V];
+#pragma unroll
+                for (int e = 0; e < V; ++e) tmp[e] = (l + e < remaining) ? xt[l + e] : from_f32<T>(0.0f);
+                memcpy(w[j], tmp, 16);
+            }
+        }
+    }
+
+    typename Op::ChanParams pu;
+    Window win;
+    if (CHMODE == CH_PT) {
+        pu = Op::uniform(a);
+    } else {
+        stage_window<Op>(sm_par, &sm_win, a.elem_offset + t0, TILE, a);
+        __syncthreads();
+        win = sm_win;
+    }
+
+    T* yt = reinterpret_cast<T*>(a.y) + t0;
+#pragma unroll
+    for (int j = 0; j < UNROLL; ++j) {
+        const uint32_t l = (uint32_t)(j * kThreads + tid) * V;
+        float f[V];
+        int code[V];
+        Pack<T, V>::unpack(w[j], f);
+        if (CHMODE == CH_PT) {
+#pragma unroll
+            for (int e = 0; e < V; ++e) f[e] = Op::template apply<CODE != 0>(f[e], pu, code[e]);
+        } else if (CHMODE == CH_VEC) {
+            uint32_t slot, rem;
+            locate(l, win, a, slot, rem);
+            typename Op::ChanParams p = Op::fetch(sm_par, a.W, slot, a);
+#pragma unroll
+            for (int e = 0; e < V; ++e) f[e] = Op::template apply<CODE != 0>(f[e], p, code[e]);
+        } else {
+            uint32_t slot, rem;
+            locate(l, win, a, slot, rem);
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                if (a.bigrow) {
+                    uint32_t jrow = (l + e) >= win.split ? 1u : 0u;
+                    slot = jrow >= a.W ? jrow - a.W : jrow;
+                }
+                typename Op::ChanParams p = Op::fetch(sm_par, a.W, slot, a);
+                f[e] = Op::template apply<CODE != 0>(f[e], p, code[e]);
+                if (!a.bigrow) {
+                    if (++rem == a.div_inner.d) { rem = 0; slot = (slot + 1 == a.W) ? 0 : slot + 1; }
+                }
+            }
+        }
+        if (full || (int64_t)l + V <= remaining) {
+            if (a.y) { Pack<T, V>::pack(f, w[j]); st_words<WORDS>(yt + l, w[j]); }
+            if (CODE != 0) st_codes<V, CODE>(a.codes, t0 + l, code);
+        } else if ((int64_t)l < remaining) {
+            const int cnt = (int)(remaining - l);
+            for (int e = 0; e < V; ++e) {
+                if (e < cnt) {
+                    if (a.y) yt[l + e] = from_f32<T>(f[e]);
+                    if (CODE == MCTQ_CODES_INT8) reinterpret_cast<uint8_t*>(a.codes)[t0 + l + e] = (uint8_t)(code[e] & 0xff);
+                }
+            }
+            if (CODE == MCTQ_CODES_INT4) {
+                uint8_t* cp = reinterpret_cast<uint8_t*>(a.codes) + ((t0 + l) >> 1);
+                for (int e = 0; e < V; e += 2) {
+                    if (e < cnt) {
+                        int hi = (e + 1 < cnt) ? code[e + 1] : 0;
+                        cp[e >> 1] = (uint8_t)((code[e] & 0xf) | ((hi & 0xf) << 4));
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ scalar fallbacks
+// Misaligned base pointers (views with odd offsets): element-per-thread, still coalesced.
+template <typename T, bool RINT>
+__global__ void __launch_bounds__(kThreads) fq_affine_scalar_kernel(const AffineArgs a) {
+    using Op = AffineOp<RINT>;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < a.n; i += stride) {
+        int64_t c = 0;
+        if (a.C > 1) c = ((a.elem_offset + i) / a.inner) % a.C;
+        typename Op::ChanParams p = a.scale ? Op::make(__ldg(a.scale + c), __ldg(a.zp + c), a) : Op::make(a.scale_val, a.zp_val, a);
+        int code;
+        float y = Op::template apply<true>(to_f32<T>(reinterpret_cast<const T*>(a.x)[i]), p, code);
+        if (a.y) reinterpret_cast<T*>(a.y)[i] = from_f32<T>(y);
+        if (a.codes) reinterpret_cast<int8_t*>(a.codes)[i] = (int8_t)code;   // scalar fallback emits INT8 only
+    }
+}
+
+// ------------------------------------------------------------------------------------------ dequant of codes
+template <int CODE>
+__global__ void __launch_bounds__(kThreads) dequant_affine_kernel(const void* codes, int is_signed, float* y, int64_t n,
+                                                                  const float* scale, const int32_t* zp, int64_t C,
+                                                                  int64_t inner, int64_t elem_offset) {
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+        int q;
+        if (CODE == MCTQ_CODES_INT8) {
+            uint8_t b = reinterpret_cast<const uint8_t*>(codes)[i];
+            q = is_signed ? (int)(int8_t)b : (int)b;
+        } else {
+            uint8_t b = reinterpret_cast<const uint8_t*>(codes)[i >> 1];
+            int nib = (i & 1) ? (b >> 4) : (b & 0xf);
+            q = is_signed ? ((nib ^ 8) - 8) : nib;
+        }
+        int64_t c = C > 1 ? ((elem_offset + i) / inner) % C : 0;
+        y[i] = __fmul_rn((float)(q - __ldg(zp + c)), __ldg(scale + c));
+    }
+}
+
+// ------------------------------------------------------------------------------------------ multi-tensor
+constexpr int kMultiTile = 2048;   // elements per tile, any dtype
+
+template <typename T>
+__device__ __forceinline__ void multi_tile_body(const MctqTensorDesc& d, int64_t e0) {
+    const T* x = reinterpret_cast<const T*>(d.x);
+    T* y = reinterpret_cast<T*>(d.y);
+    const int64_t e1 = min(e0 + (int64_t)kMultiTile, d.n);
+    const bool fast = (d.qmax - d.qmin) < kFastRangeLimit;
+    AffineArgs a;
+    a.qmin = d.qmin;
+    a.qmax = d.qmax;
+    // 8 elements per thread, strided by the CTA width so that every access is coalesced
+    float xv[kMultiTile / kThreads];
+#pragma unroll
+    for (int k = 0; k < kMultiTile / kThreads; ++k) {
+        int64_t i = e0 + k * kThreads + threadIdx.x;
+        xv[k] = i < e1 ? to_f32<T>(x[i]) : 0.0f;
+    }
+#pragma unroll
+    for (int k = 0; k < kMultiTile / kThreads; ++k) {
+        int64_t i = e0 + k * kThreads + threadIdx.x;
+        if (i < e1) {
+            int64_t c = d.C > 1 ? (i / d.inner) % d.C : 0;
+            float s = __ldg(d.scale + c);
+            int zp = __ldg(d.zp + c);
+            int code;
+            float out;
+            if (fast) out = AffineOp<false>::apply<true>(xv[k], AffineOp<false>::make(s, zp, a), code);
+            else out = AffineOp<true>::apply<true>(xv[k], AffineOp<true>::make(s, zp, a), code);
+            if (y) y[i] = from_f32<T>(out);
+            if (d.codes && d.code_mode == MCTQ_CODES_INT8) reinterpret_cast<uint8_t*>(d.codes)[i] = (uint8_t)(code & 0xff);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) fq_affine_multi_kernel(const MctqTensorDesc* __restrict__ descs,
+                                                                   const int32_t* __restrict__ tile_starts, int n_desc) {
+    // which tensor does this tile belong to?  upper-bound binary search over tile_starts
+    const int tile = blockIdx.x;
+    int lo = 0, hi = n_desc;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (__ldg(tile_starts + mid) <= tile) lo = mid; else hi = mid;
+    }
+    const MctqTensorDesc d = descs[lo];
+    const int64_t e0 = (int64_t)(tile - __ldg(tile_starts + lo)) * kMultiTile;
+    if (d.dtype == MCTQ_F32) multi_tile_body<float>(d, e0);
+    else if (d.dtype == MCTQ_BF16) multi_tile_body<__nv_bfloat16>(d, e0);
+    else multi_tile_body<__half>(d, e0);
+}
+
+}  // namespace mctq
+
+using namespace mctq;
+
+namespace {
+
+int check_codes(int32_t qmin, int32_t qmax, int code_mode, const void* codes) {
+    if (code_mode == MCTQ_CODES_NONE) return 0;
+    if (!codes) return MCTQ_E_BADARG;
+    if (code_mode == MCTQ_CODES_INT8) {
+        if ((qmin >= -128 && qmax <= 127) || (qmin >= 0 && qmax <= 255)) return 0;
+        return MCTQ_E_RANGE;
+    }
+    if (code_mode == MCTQ_CODES_INT4) {
+        if ((qmin >= -8 && qmax <= 7) || (qmin >= 0 && qmax <= 15)) return 0;
+        return MCTQ_E_RANGE;
+    }
+    return MCTQ_E_BADARG;
+}
+
+template <typename T, int CHMODE, int CODE, int UNROLL, bool RINT>
+int launch_affine_tiles(const AffineArgs& a_in, cudaStream_t st) {
+    constexpr int V = 16 / sizeof(T);
+    constexpr uint32_t TILE = kThreads * UNROLL * V;
+    AffineArgs a = a_in;
+    size_t smem = 0;
+    if (CHMODE != CH_PT) {
+        set_window(a, TILE);
+        smem = (size_t)a.W * 3 * sizeof(float);
+        int rc = ensure_smem(fq_affine_kernel<T, CHMODE, CODE, UNROLL, RINT>, smem);
+        if (rc) return rc;
+    }
+    int64_t tiles = (a.n + TILE - 1) / TILE;
+    if (tiles > 0x7fffffffLL) return MCTQ_E_BADARG;
+    fq_affine_kernel<T, CHMODE, CODE, UNROLL, RINT><<<(unsigned)tiles, kThreads, smem, st>>>(a);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cuda_rc(cudaGetLastError());
+}
+
+template <typename T, int CHMODE, int CODE, bool RINT>
+int launch_affine_unroll(const AffineArgs& a, cudaStream_t st) {
+    // the unroll sweep (mctq_set_tuning key 0) exists only for the plain fake-quant variants
+    if (CODE == MCTQ_CODES_NONE && !RINT) {
+        if (g_unroll == 2) return launch_affine_tiles<T, CHMODE, MCTQ_CODES_NONE, 2, false>(a, st);
+        if (g_unroll == 8) return launch_affine_tiles<T, CHMODE, MCTQ_CODES_NONE, 8, false>(a, st);
+    }
+    return launch_affine_tiles<T, CHMODE, CODE, 4, RINT>(a, st);
+}
+
+template <typename T, int CHMODE, bool RINT>
+int launch_affine_code(const AffineArgs& a, int code_mode, cudaStream_t st) {
+    switch (code_mode) {
+        case MCTQ_CODES_INT8: return launch_affine_unroll<T, CHMODE, MCTQ_CODES_INT8, RINT>(a, st);
+        case MCTQ_CODES_INT4: return launch_affine_unroll<T, CHMODE, MCTQ_CODES_INT4, RINT>(a, st);
+        default: return launch_affine_unroll<T, CHMODE, MCTQ_CODES_NONE, RINT>(a, st);
+    }
+}
+
+template <typename T>
+int launch_affine_typed(const AffineArgs& a, int code_mode, cudaStream_t st) {
+    constexpr int V = 16 / sizeof(T);
+    const bool rint_path = g_force_rint || !(a.qmax - (int64_t)a.qmin < kFastRangeLimit);
+    // vector path needs 16-byte aligned x / y and suitably aligned codes
+    bool vec_ok = aligned16(a.x) && (!a.y || aligned16(a.y));
+    if (code_mode != MCTQ_CODES_NONE) vec_ok = vec_ok && (reinterpret_cast<uintptr_t>(a.codes) & 7u) == 0;
+    if (!vec_ok) {
+        if (code_mode == MCTQ_CODES_INT4) return MCTQ_E_BADARG;
+        int64_t blocks = (a.n + kThreads - 1) / kThreads;
+        if (blocks > 148 * 64) blocks = 148 * 64;
+        if (rint_path) fq_affine_scalar_kernel<T, true><<<(unsigned)blocks, kThreads, 0, st>>>(a);
+        else fq_affine_scalar_kernel<T, false><<<(unsigned)blocks, kThreads, 0, st>>>(a);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return cuda_rc(cudaGetLastError());
+    }
+    int chmode;
+    if (a.C == 1) chmode = CH_PT;
+    else if (a.inner % V == 0 && a.elem_offset % V == 0) chmode = CH_VEC;
+    else chmode = CH_ELEM;
+#define MCTQ_DISPATCH_AFF(CM)                                                                   \
+    return rint_path ? launch_affine_code<T, CM, true>(a, code_mode, st) : launch_affine_code<T, CM, false>(a, code_mode, st)
+    if (chmode == CH_PT) { MCTQ_DISPATCH_AFF(CH_PT); }
+    if (chmode == CH_VEC) { MCTQ_DISPATCH_AFF(CH_VEC); }
+    MCTQ_DISPATCH_AFF(CH_ELEM);
+#undef MCTQ_DISPATCH_AFF
+}
+
+int launch_affine(const AffineArgs& a, int x_dtype, int code_mode, cudaStream_t st) {
+    if (a.n < 0 || a.C < 1 || a.inner < 1 || a.elem_offset < 0 || !a.x || (!a.y && code_mode == MCTQ_CODES_NONE))
+        return MCTQ_E_BADARG;
+    if (a.qmin > a.qmax) return MCTQ_E_RANGE;
+    int rc = check_codes(a.qmin, a.qmax, code_mode, a.codes);
+    if (rc) return rc;
+    if (a.n == 0) return 0;
+    switch (x_dtype) {
+        case MCTQ_F32: return launch_affine_typed<float>(a, code_mode, st);
+        case MCTQ_BF16: return launch_affine_typed<__nv_bfloat16>(a, code_mode, st);
+        case MCTQ_F16: return launch_affine_typed<__half>(a, code_mode, st);
+        default: return MCTQ_E_DTYPE;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int mctq_fq_affine(const void* x, void* y, void* codes, int64_t n, int x_dtype, const float* scale, const int32_t* zp,
+                   int64_t C, int64_t inner, int64_t elem_offset, int32_t qmin, int32_t qmax, int code_mode,
+                   void* stream) {
+    if (!scale || !zp) return MCTQ_E_BADARG;
+    AffineArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x = x; a.y = y; a.codes = codes; a.n = n; a.scale = scale; a.zp = zp;
+    a.C = C; a.inner = C == 1 ? 1 : inner; a.elem_offset = C == 1 ? 0 : elem_offset; a.qmin = qmin; a.qmax = qmax;
+    return launch_affine(a, x_dtype, code_mode, (cudaStream_t)stream);
+}
+
+int mctq_fq_affine_scalar(const void* x, void* y, void* codes, int64_t n, int x_dtype, float scale, int32_t zp,
+                          int32_t qmin, int32_t qmax, int code_mode, void* stream) {
+    AffineArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x = x; a.y = y; a.codes = codes; a.n = n; a.scale = nullptr; a.zp = nullptr; a.scale_val = scale; a.zp_val = zp;
+    a.C = 1; a.inner = 1; a.elem_offset = 0; a.qmin = qmin; a.qmax = qmax;
+    return launch_affine(a, x_dtype, code_mode, (cudaStream_t)stream);
+}
+
+int mctq_dequant_affine(const void* codes, int code_mode, int is_signed, float* y, int64_t n, const float* scale,
+                        const int32_t* zp, int64_t C, int64_t inner, int64_t elem_offset, void* stream) {
+    if (!codes || !y || !scale || !zp || n < 0 || C < 1 || inner < 1) return MCTQ_E_BADARG;
+    if (n == 0) return 0;
+    int64_t blocks = (n + kThreads - 1) / kThreads;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (code_mode == MCTQ_CODES_INT8)
+        dequant_affine_kernel<MCTQ_CODES_INT8><<<(unsigned)blocks, kThreads, 0, st>>>(codes, is_signed, y, n, scale, zp, C, inner, elem_offset);
+    else if (code_mode == MCTQ_CODES_INT4)
+        dequant_affine_kernel<MCTQ_CODES_INT4><<<(unsigned)blocks, kThreads, 0, st>>>(codes, is_signed, y, n, scale, zp, C, inner, elem_offset);
+    else return MCTQ_E_BADARG;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cuda_rc(cudaGetLastError());
+}
+
+int64_t mctq_multi_tile_elems(void) { return kMultiTile; }
+
+int64_t mctq_multi_plan(const MctqTensorDesc* descs, int n_desc, int32_t* tile_starts) {
+    if (!descs || !tile_starts || n_desc < 0) return MCTQ_E_BADARG;
+    int64_t t = 0;
+    for (int k = 0; k < n_desc; ++k) {
+        if (descs[k].n < 0) return MCTQ_E_BADARG;
+        tile_starts[k] = (int32_t)t;
+        t += (descs[k].n + kMultiTile - 1) / kMultiTile;
+        if (t > 0x7fffffffLL) return MCTQ_E_BADARG;
+    }
+    tile_starts[n_desc] = (int32_t)t;
+    return t;
+}
+
+int mctq_fq_affine_multi(const MctqTensorDesc* descs_dev, const int32_t* tile_starts_dev, int n_desc,
+                         int64_t total_tiles, void* stream) {
+    if (!descs_dev || !tile_starts_dev || n_desc < 1 || total_tiles < 0 || total_tiles > 0x7fffffffLL) return MCTQ_E_BADARG;
+    if (total_tiles == 0) return 0;
+    fq_affine_multi_kernel<<<(unsigned)total_tiles, kThreads, 0, (cudaStream_t)stream>>>(descs_dev, tile_starts_dev, n_desc);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cuda_rc(cudaGetLastError());
+}
+
+}  // extern "C"

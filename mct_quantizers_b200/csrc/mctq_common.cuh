@@ -1,0 +1,251 @@
+// mctq_common.cuh -- shared device utilities of libmctq_sm100 (see mctq_affine.cu / mctq_lut.cu / mctq_host.cu).
+// Build: mct_quantizers_b200/build.py
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo --fmad=false ... (one object per .cu, linked into one .so)
+// (--fmad=false: the reference never contracts a multiply-add; the fused operations these kernels need are
+//  written explicitly with __fmaf_rn, which the flag does not touch.)
+//
+// All kernels are HBM-bound streaming kernels (no tensor cores): one CTA = one tile of kThreads * UNROLL vectors,
+// every load of the tile is issued before the first use, per-channel parameters of the rows the tile touches are
+// staged in shared memory while the loads are in flight.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "mctq.h"
+
+namespace mctq {
+
+constexpr int kThreads = 256;
+
+// process-wide state (defined in mctq_host.cu)
+extern std::atomic<int64_t> g_launches;
+extern int g_unroll;
+extern int g_force_rint;
+extern int g_force_ieee_div;
+
+enum ChMode { CH_PT = 0, CH_VEC = 1, CH_ELEM = 2 };
+
+// ------------------------------------------------------------------------------------------ small utils
+struct FastDiv {   // floor(u / d) for 0 <= u < 2^31, 1 <= d < 2^31  (round-up multiplier, Granlund-Montgomery)
+    uint32_t mul, shift, d;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f;
+    f.d = d;
+    uint32_t s = 0;
+    while (s < 32 && (1ull << s) < d) ++s;
+    f.shift = s;
+    f.mul = (uint32_t)((((1ull << 32) * ((1ull << s) - d)) / d) + 1);
+    return f;
+}
+__device__ __forceinline__ uint32_t fdiv_u32(uint32_t u, const FastDiv& f) {
+    return (__umulhi(u, f.mul) + u) >> f.shift;
+}
+
+template <int BYTES> struct Vec;
+template <> struct Vec<16> { using type = uint4; };
+template <> struct Vec<8> { using type = uint2; };
+template <> struct Vec<4> { using type = uint32_t; };
+template <> struct Vec<2> { using type = uint16_t; };
+template <> struct Vec<1> { using type = uint8_t; };
+
+// streaming loads: read-only path, do not allocate in L1 (every byte is touched exactly once)
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint2 ld_stream(const uint2* p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream(uint4* p, const uint4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_stream(uint2* p, const uint2& v) {
+    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void st_stream(uint32_t* p, const uint32_t& v) {
+    asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_stream(uint16_t* p, const uint16_t& v) {
+    asm volatile("st.global.L1::no_allocate.u16 [%0], %1;" :: "l"(p), "h"(v) : "memory");
+}
+
+// element <-> f32
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+
+// unpack a register-resident vector of V elements of T (V * sizeof(T) bytes, as 32-bit words) to floats
+template <typename T, int V> struct Pack;
+template <int V> struct Pack<float, V> {
+    static constexpr int kWords = V;
+    __device__ static __forceinline__ void unpack(const uint32_t* w, float* f) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) f[i] = __uint_as_float(w[i]);
+    }
+    __device__ static __forceinline__ void pack(const float* f, uint32_t* w) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) w[i] = __float_as_uint(f[i]);
+    }
+};
+template <int V> struct Pack<__nv_bfloat16, V> {
+    static constexpr int kWords = V / 2;
+    __device__ static __forceinline__ void unpack(const uint32_t* w, float* f) {
+#pragma unroll
+        for (int i = 0; i < V / 2; ++i) {
+            f[2 * i] = __uint_as_float(w[i] << 16);
+            f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    }
+    __device__ static __forceinline__ void pack(const float* f, uint32_t* w) {
+#pragma unroll
+        for (int i = 0; i < V / 2; ++i) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+    }
+};
+template <int V> struct Pack<__half, V> {
+    static constexpr int kWords = V / 2;
+    __device__ static __forceinline__ void unpack(const uint32_t* w, float* f) {
+#pragma unroll
+        for (int i = 0; i < V / 2; ++i) {
+            __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
+            float2 v = __half22float2(h);
+            f[2 * i] = v.x;
+            f[2 * i + 1] = v.y;
+        }
+    }
+    __device__ static __forceinline__ void pack(const float* f, uint32_t* w) {
+#pragma unroll
+        for (int i = 0; i < V / 2; ++i) {
+            __half2 h = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+    }
+};
+
+template <int WORDS> __device__ __forceinline__ void ld_words(const void* p, uint32_t* w);
+template <> __device__ __forceinline__ void ld_words<4>(const void* p, uint32_t* w) {
+    uint4 v = ld_stream(reinterpret_cast<const uint4*>(p));
+    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+}
+template <> __device__ __forceinline__ void ld_words<2>(const void* p, uint32_t* w) {
+    uint2 v = ld_stream(reinterpret_cast<const uint2*>(p));
+    w[0] = v.x; w[1] = v.y;
+}
+template <int WORDS> __device__ __forceinline__ void st_words(void* p, const uint32_t* w);
+template <> __device__ __forceinline__ void st_words<4>(void* p, const uint32_t* w) {
+    st_stream(reinterpret_cast<uint4*>(p), make_uint4(w[0], w[1], w[2], w[3]));
+}
+template <> __device__ __forceinline__ void st_words<2>(void* p, const uint32_t* w) {
+    st_stream(reinterpret_cast<uint2*>(p), make_uint2(w[0], w[1]));
+}
+
+// integer codes of one vector -> global.  INT8: V bytes; INT4: V/2 bytes (element 2j in the low nibble)
+template <int V, int CODE> __device__ __forceinline__ void st_codes(void* codes, int64_t elem, const int* c) {
+    if (CODE == MCTQ_CODES_INT8) {
+        uint32_t w[V / 4];
+#pragma unroll
+        for (int i = 0; i < V / 4; ++i)
+            w[i] = (uint32_t)(c[4 * i] & 0xff) | ((uint32_t)(c[4 * i + 1] & 0xff) << 8) |
+                   ((uint32_t)(c[4 * i + 2] & 0xff) << 16) | ((uint32_t)(c[4 * i + 3] & 0xff) << 24);
+        uint8_t* p = reinterpret_cast<uint8_t*>(codes) + elem;
+        if (V == 4) st_stream(reinterpret_cast<uint32_t*>(p), w[0]);
+        else st_stream(reinterpret_cast<uint2*>(p), make_uint2(w[0], w[V / 4 - 1]));
+    } else if (CODE == MCTQ_CODES_INT4) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int i = 0; i < V; ++i) w |= (uint32_t)(c[i] & 0xf) << (4 * i);
+        uint8_t* p = reinterpret_cast<uint8_t*>(codes) + (elem >> 1);
+        if (V == 4) st_stream(reinterpret_cast<uint16_t*>(p), (uint16_t)w);
+        else st_stream(reinterpret_cast<uint32_t*>(p), w);
+    }
+}
+// ------------------------------------------------------------------------------------------ channel window
+// A tile covers logical elements [g0, g0 + tile) of the [outer][C][inner] view.  It touches rows
+// r0 .. r0 + nr - 1 (row = g / inner, channel = row % C).  Slot jj of the window holds channel (r0 + jj) % C,
+// for jj < W = min(max rows per tile, C); row j of the tile maps to slot j % W.
+struct Window {
+    uint32_t off0;     // offset of g0 inside its row (bigrow: unused)
+    uint32_t split;    // bigrow: first local element of the second row (or > tile if none)
+};
+
+template <class Op>
+__device__ __forceinline__ void stage_window(float* sm_par, Window* sm_win, int64_t g0, uint32_t tile_elems,
+                                             const typename Op::Args& a) {
+    const uint32_t tid = threadIdx.x;
+    if (tid < a.W || tid == 0) {
+        int64_t r0 = g0 / a.inner;
+        int64_t off = g0 - r0 * a.inner;
+        if (tid == 0) {
+            Window w;
+            w.off0 = a.bigrow ? 0u : (uint32_t)off;
+            int64_t sp = a.inner - off;
+            w.split = (uint32_t)(sp > (int64_t)tile_elems ? (int64_t)tile_elems + 1 : sp);
+            *sm_win = w;
+        }
+        int64_t c0 = r0 % a.C;
+        for (uint32_t jj = tid; jj < a.W; jj += kThreads) {
+            int64_t c = c0 + jj;
+            c = c % a.C;
+            Op::stage(sm_par, a.W, jj, c, a);
+        }
+    }
+}
+
+// row (slot) of local element l
+template <class Args>
+__device__ __forceinline__ void locate(uint32_t l, const Window& w, const Args& a, uint32_t& slot, uint32_t& rem) {
+    uint32_t j;
+    if (a.bigrow) {
+        j = l >= w.split ? 1u : 0u;
+        rem = 0;   // unused in bigrow mode
+    } else {
+        uint32_t u = w.off0 + l;
+        j = fdiv_u32(u, a.div_inner);
+        rem = u - j * a.div_inner.d;
+    }
+    slot = j - fdiv_u32(j, a.div_W) * a.div_W.d;
+}
+
+
+// ------------------------------------------------------------------------------------------ host helpers
+inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? 0 : (int)e; }
+
+template <typename K>
+int ensure_smem(K kernel, size_t bytes) {
+    if (bytes <= 48 * 1024) return 0;
+    if (bytes > 200 * 1024) return MCTQ_E_BADARG;
+    return cuda_rc(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// geometry of the channel window for a tile of `tile` elements
+template <class Args>
+void set_window(Args& a, uint32_t tile) {
+    a.bigrow = a.inner >= (int64_t)tile ? 1u : 0u;
+    int64_t rows = a.bigrow ? 2 : (int64_t)tile / a.inner + 2;
+    a.W = (uint32_t)(rows < a.C ? rows : a.C);
+    a.div_inner = make_fastdiv(a.bigrow ? 1u : (uint32_t)a.inner);
+    a.div_W = make_fastdiv(a.W);
+}
+
+}  // namespace mctq

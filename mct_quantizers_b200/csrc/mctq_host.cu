@@ -1,0 +1,165 @@
+// mctq_host.cu -- process-wide state, introspection entry points and the host-buffer (staged) operators.
+#include "mctq_common.cuh"
+
+namespace mctq {
+std::atomic<int64_t> g_launches{0};
+int g_unroll = 4;
+int g_force_rint = 0;
+int g_force_ieee_div = 0;
+}  // namespace mctq
+
+using namespace mctq;
+
+extern "C" {
+
+int mctq_abi_version(void) { return MCTQ_ABI_VERSION; }
+
+const char* mctq_build_info(void) {
+    return "libmctq_sm100 abi=1 arch=sm_100a threads=256 vec=16B unroll={2,4,8} fmad=off";
+}
+
+int64_t mctq_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int mctq_set_tuning(int key, int value) {
+    int prev;
+    switch (key) {
+        case 0: prev = g_unroll; if (value != 2 && value != 4 && value != 8) return MCTQ_E_BADARG; g_unroll = value; return prev;
+        case 1: prev = g_force_rint; g_force_rint = value ? 1 : 0; return prev;
+        case 2: prev = g_force_ieee_div; g_force_ieee_div = value ? 1 : 0; return prev;
+        default: return MCTQ_E_BADARG;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- host staging
+namespace {
+constexpr int kHostStreams = 3;
+constexpr size_t kHostChunkBytesIn = 32u << 20;      // input bytes per chunk
+struct HostCtx {
+    int device = -1;
+    cudaStream_t st[kHostStreams] = {nullptr, nullptr, nullptr};
+};
+HostCtx g_hctx[16];
+
+int host_ctx(int device, HostCtx** out) {
+    if (device < 0 || device >= 16) return MCTQ_E_NODEVICE;
+    HostCtx& c = g_hctx[device];
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return (int)e;
+    if (c.device != device) {
+        for (int i = 0; i < kHostStreams; ++i) {
+            e = cudaStreamCreateWithFlags(&c.st[i], cudaStreamNonBlocking);
+            if (e != cudaSuccess) return (int)e;
+        }
+        c.device = device;
+    }
+    *out = &c;
+    return 0;
+}
+size_t dtype_size(int dt) { return dt == MCTQ_F32 ? 4 : 2; }
+}  // namespace
+
+size_t mctq_host_staging_min_bytes(void) {
+    // per stream: one input chunk + one f32-sized output chunk (LUT output of a 2-byte input is 2x larger) + parameter area
+    return kHostStreams * (kHostChunkBytesIn + 2 * kHostChunkBytesIn) + (4u << 20);
+}
+
+int mctq_fq_affine_host(const void* x_host, void* y_host, int64_t n, int x_dtype, const float* scale_host,
+                        const int32_t* zp_host, int64_t C, int64_t inner, int32_t qmin, int32_t qmax,
+                        void* staging_dev, size_t staging_bytes, int device) {
+    if (!x_host || !y_host || !scale_host || !zp_host || !staging_dev || n < 0 || C < 1 || inner < 1) return MCTQ_E_BADARG;
+    if (x_dtype < 0 || x_dtype > 2) return MCTQ_E_DTYPE;
+    if (staging_bytes < mctq_host_staging_min_bytes() || (size_t)C * 8 > (4u << 20)) return MCTQ_E_BADARG;
+    HostCtx* ctx;
+    int rc = host_ctx(device, &ctx);
+    if (rc) return rc;
+    const size_t es = dtype_size(x_dtype);
+    uint8_t* base = reinterpret_cast<uint8_t*>(staging_dev);
+    float* d_scale = reinterpret_cast<float*>(base);
+    int32_t* d_zp = reinterpret_cast<int32_t*>(base + (2u << 20));
+    uint8_t* slots = base + (4u << 20);
+    cudaError_t e;
+    // parameters go first on stream 0; the other streams wait for them through an event
+    e = cudaMemcpyAsync(d_scale, scale_host, (size_t)C * 4, cudaMemcpyHostToDevice, ctx->st[0]);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemcpyAsync(d_zp, zp_host, (size_t)C * 4, cudaMemcpyHostToDevice, ctx->st[0]);
+    if (e != cudaSuccess) return (int)e;
+    cudaEvent_t ev;
+    e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) return (int)e;
+    cudaEventRecord(ev, ctx->st[0]);
+    for (int i = 1; i < kHostStreams; ++i) cudaStreamWaitEvent(ctx->st[i], ev, 0);
+    const int64_t chunk_elems = (int64_t)(kHostChunkBytesIn / es);
+    int k = 0;
+    for (int64_t off = 0; off < n; off += chunk_elems, ++k) {
+        const int64_t cnt = (n - off) < chunk_elems ? (n - off) : chunk_elems;
+        cudaStream_t st = ctx->st[k % kHostStreams];
+        uint8_t* d_in = slots + (size_t)(k % kHostStreams) * 3 * kHostChunkBytesIn;
+        uint8_t* d_out = d_in + kHostChunkBytesIn;
+        e = cudaMemcpyAsync(d_in, reinterpret_cast<const uint8_t*>(x_host) + off * es, cnt * es, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) break;
+        rc = mctq_fq_affine(d_in, d_out, nullptr, cnt, x_dtype, d_scale, d_zp, C, inner, off, qmin, qmax, MCTQ_CODES_NONE, st);
+        if (rc) break;
+        e = cudaMemcpyAsync(reinterpret_cast<uint8_t*>(y_host) + off * es, d_out, cnt * es, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) break;
+    }
+    for (int i = 0; i < kHostStreams; ++i) {
+        cudaError_t e2 = cudaStreamSynchronize(ctx->st[i]);
+        if (e == cudaSuccess && e2 != cudaSuccess) e = e2;
+    }
+    cudaEventDestroy(ev);
+    if (rc) return rc;
+    return cuda_rc(e);
+}
+
+int mctq_fq_lut_host(const void* x_host, float* y_host, int64_t n, int x_dtype, const void* table_host, int K,
+                     const float* thr_host, int64_t C, int64_t inner, float eps, int scalar_mode, float divisor,
+                     float thr_f32, int round_to_x_dtype, void* staging_dev, size_t staging_bytes, int device) {
+    if (!x_host || !y_host || !table_host || !staging_dev || n < 0 || C < 1 || inner < 1) return MCTQ_E_BADARG;
+    if (!scalar_mode && !thr_host) return MCTQ_E_BADARG;
+    if (x_dtype < 0 || x_dtype > 2) return MCTQ_E_DTYPE;
+    const size_t tbytes = mctq_lut_table_bytes(K);
+    if (!tbytes || tbytes > (1u << 20)) return MCTQ_E_LUT;
+    if (staging_bytes < mctq_host_staging_min_bytes() || (size_t)C * 4 > (2u << 20)) return MCTQ_E_BADARG;
+    HostCtx* ctx;
+    int rc = host_ctx(device, &ctx);
+    if (rc) return rc;
+    const size_t es = dtype_size(x_dtype);
+    uint8_t* base = reinterpret_cast<uint8_t*>(staging_dev);
+    float* d_thr = reinterpret_cast<float*>(base);
+    uint8_t* d_table = base + (2u << 20);
+    uint8_t* slots = base + (4u << 20);
+    cudaError_t e = cudaSuccess;
+    if (!scalar_mode) e = cudaMemcpyAsync(d_thr, thr_host, (size_t)C * 4, cudaMemcpyHostToDevice, ctx->st[0]);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemcpyAsync(d_table, table_host, tbytes, cudaMemcpyHostToDevice, ctx->st[0]);
+    if (e != cudaSuccess) return (int)e;
+    cudaEvent_t ev;
+    e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) return (int)e;
+    cudaEventRecord(ev, ctx->st[0]);
+    for (int i = 1; i < kHostStreams; ++i) cudaStreamWaitEvent(ctx->st[i], ev, 0);
+    const int64_t chunk_elems = (int64_t)(kHostChunkBytesIn / 4);   // output chunk is f32: bound by it
+    int k = 0;
+    for (int64_t off = 0; off < n; off += chunk_elems, ++k) {
+        const int64_t cnt = (n - off) < chunk_elems ? (n - off) : chunk_elems;
+        cudaStream_t st = ctx->st[k % kHostStreams];
+        uint8_t* d_in = slots + (size_t)(k % kHostStreams) * 3 * kHostChunkBytesIn;
+        float* d_out = reinterpret_cast<float*>(d_in + kHostChunkBytesIn);
+        e = cudaMemcpyAsync(d_in, reinterpret_cast<const uint8_t*>(x_host) + off * es, cnt * es, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) break;
+        if (scalar_mode) rc = mctq_fq_lut_scalar(d_in, d_out, nullptr, cnt, x_dtype, d_table, K, divisor, thr_f32, round_to_x_dtype, MCTQ_CODES_NONE, st);
+        else rc = mctq_fq_lut(d_in, d_out, nullptr, cnt, x_dtype, d_table, K, d_thr, C, inner, off, eps, MCTQ_CODES_NONE, st);
+        if (rc) break;
+        e = cudaMemcpyAsync(y_host + off, d_out, cnt * 4, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) break;
+    }
+    for (int i = 0; i < kHostStreams; ++i) {
+        cudaError_t e2 = cudaStreamSynchronize(ctx->st[i]);
+        if (e == cudaSuccess && e2 != cudaSuccess) e = e2;
+    }
+    cudaEventDestroy(ev);
+    if (rc) return rc;
+    return cuda_rc(e);
+}
+
+}  // extern "C"

@@ -1,0 +1,503 @@
+"""torch.library operators of the `mctq` namespace: the boundary between the quantizer objects and the
+sm_100a kernels.
+
+    torch.ops.mctq.fq_affine_scalar   <- torch.fake_quantize_per_tensor_affine(x, float, int, qmin, qmax)
+    torch.ops.mctq.fq_affine_tensor   <- torch.fake_quantize_per_tensor_affine(x, Tensor[1], Tensor[1], qmin, qmax)
+    torch.ops.mctq.fq_affine_channel  <- torch.fake_quantize_per_channel_affine(x, scale, zp, axis, qmin, qmax)
+    torch.ops.mctq.fq_lut_tensor      <- lut_quantizer(..., threshold=Tensor, per_channel, channel_axis, input_rank)
+    torch.ops.mctq.fq_lut_scalar      <- lut_quantizer(..., threshold=float)            (activations)
+    torch.ops.mctq.quantize_affine_*  -> integer codes (+ optional fake-quant values); mctq.dequantize_affine
+
+(reference call sites: see include/mctq.h).  Each op has a CUDA implementation (device pointers + the
+caller's current stream into the C ABI, no synchronisation), a CPU-tensor implementation that streams the
+host buffer through the GPU (mctq_fq_*_host), and a fake/meta implementation so that fx tracing,
+torch.compile and shape propagation work.  There is no eager / CPU arithmetic fallback anywhere.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from mct_quantizers_b200 import _native
+from mct_quantizers_b200._native import MctqError, c_vp
+
+_DT = {torch.float32: _native.F32, torch.bfloat16: _native.BF16, torch.float16: _native.F16}
+
+_LIB = torch.library.Library("mctq", "DEF")
+_LIB.define("fq_affine_scalar(Tensor x, float scale, int zero_point, int quant_min, int quant_max) -> Tensor")
+_LIB.define("fq_affine_tensor(Tensor x, Tensor scale, Tensor zero_point, int quant_min, int quant_max) -> Tensor")
+_LIB.define("fq_affine_channel(Tensor x, Tensor scale, Tensor zero_point, int axis, int quant_min, int quant_max) -> Tensor")
+_LIB.define("fq_lut_tensor(Tensor x, Tensor table, int K, Tensor threshold, bool per_channel, int axis, float eps) -> Tensor")
+_LIB.define("fq_lut_scalar(Tensor x, Tensor table, int K, float divisor, float threshold, bool round_to_input_dtype) -> Tensor")
+_LIB.define("quantize_affine_channel(Tensor x, Tensor scale, Tensor zero_point, int axis, int quant_min, int quant_max, "
+            "int code_mode, bool want_values) -> (Tensor, Tensor)")
+_LIB.define("dequantize_affine(Tensor codes, int code_mode, bool is_signed, int[] shape, Tensor scale, Tensor zero_point, "
+            "int axis) -> Tensor")
+_LIB.define("lut_indices(Tensor x, Tensor table, int K, Tensor threshold, bool per_channel, int axis, float eps, "
+            "int idx_mode) -> Tensor")
+
+
+# --------------------------------------------------------------------------------------------- helpers
+def _dtype_tag(x):
+    try:
+        return _DT[x.dtype]
+    except KeyError:
+        raise NotImplementedError(f'"mctq_fake_quantize" not implemented for \'{x.dtype}\' '
+                                  f'(float32, bfloat16 and float16 are supported)') from None
+
+
+def _ptr(t):
+    return c_vp(t.data_ptr()) if t is not None else None
+
+
+def _stream(device):
+    return c_vp(torch.cuda.current_stream(device).cuda_stream)
+
+
+class _on_device:
+    """Make `device` current for the duration of a launch (kernels launch on the current device)."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, device):
+        self.idx = device.index if device.index is not None else torch.cuda.current_device()
+
+    def __enter__(self):
+        self.prev = torch.cuda.current_device()
+        if self.prev != self.idx:
+            torch.cuda.set_device(self.idx)
+
+    def __exit__(self, *exc):
+        if self.prev != self.idx:
+            torch.cuda.set_device(self.prev)
+
+
+def _dense(x):
+    """x itself when its memory is one dense block (any permutation of strides), else a contiguous copy."""
+    if x.is_contiguous() or x.numel() == 0:
+        return x
+    if x.is_non_overlapping_and_dense():
+        return x
+    return x.contiguous()
+
+
+def _channel_layout(x, axis):
+    """(x_dense, C, inner): the [outer][C][inner] view in MEMORY order.  For a permuted-but-dense tensor
+    (e.g. channels_last) the channel axis keeps its meaning; only `inner` changes."""
+    nd = x.dim()
+    if not -nd <= axis < nd:
+        raise IndexError(f"Dimension out of range (expected to be in range of [{-nd}, {nd - 1}], but got {axis})")
+    axis %= nd
+    x = _dense(x)
+    C = x.shape[axis]
+    if x.is_contiguous():
+        inner = 1
+        for s in x.shape[axis + 1:]:
+            inner *= int(s)
+        return x, int(C), inner
+    # dense, permuted: dims that sit "inside" the channel axis in memory are those with a smaller stride
+    # -- valid only if they tile the channel stride exactly
+    strides, shape = x.stride(), x.shape
+    inner = 1
+    for d in range(nd):
+        if d != axis and shape[d] > 1 and strides[d] < strides[axis]:
+            inner *= int(shape[d])
+    if C > 1 and strides[axis] != inner:
+        x = x.contiguous()
+        return _channel_layout(x, axis)
+    return x, int(C), inner
+
+
+def _check_range(qmin, qmax):
+    if qmin > qmax:
+        raise RuntimeError("`quant_min` should be less than or equal to `quant_max`.")
+
+
+def _check_channel_params(x, scale, zp, axis):
+    if scale.dtype != torch.float32:
+        raise RuntimeError(f"Scale must be Float, found {scale.dtype}")
+    if zp.dtype != torch.int32:
+        raise RuntimeError(f"Zero-point must be Int32, found {zp.dtype}")
+    if scale.dim() != 1 or zp.dim() != 1:
+        raise RuntimeError("scale and zero-point need to be 1-D tensors")
+    nd = x.dim()
+    if not -nd <= axis < nd:
+        raise RuntimeError("`axis` must be between 0 and number of dimensions of input")
+    if scale.numel() != x.shape[axis] or zp.numel() != x.shape[axis]:
+        raise RuntimeError("dimensions of scale and zero-point are not consistent with input tensor")
+
+
+def _param_on(t, device):
+    return t if t.device == device else t.to(device, non_blocking=True)
+
+
+_staging = {}
+
+
+def _staging_buffer(device_index):
+    buf = _staging.get(device_index)
+    if buf is None:
+        nbytes = _native.load().mctq_host_staging_min_bytes()
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=torch.device("cuda", device_index))
+        _staging[device_index] = buf
+    return buf
+
+
+def _require_cuda_for_host_path():
+    if not torch.cuda.is_available():
+        raise MctqError("mct_quantizers_b200 received a CPU tensor but no CUDA device is available: the package "
+                        "has no CPU arithmetic path (host tensors are streamed through the GPU)")
+    return torch.cuda.current_device()
+
+
+def _host_array(t, dtype):
+    return np.ascontiguousarray(t.detach().cpu().numpy().astype(dtype, copy=False).reshape(-1))
+
+
+# --------------------------------------------------------------------------------------------- CUDA impls
+def _affine_scalar_cuda(x, scale, zero_point, quant_min, quant_max):
+    tag = _dtype_tag(x)
+    _check_range(quant_min, quant_max)
+    if not quant_min <= zero_point <= quant_max:
+        raise RuntimeError("`zero_point` must be between `quant_min` and `quant_max`.")
+    xd = _dense(x)
+    y = torch.empty_like(xd)
+    if xd.numel():
+        lib = _native.load()
+        with _on_device(xd.device):
+            rc = lib.mctq_fq_affine_scalar(_ptr(xd), _ptr(y), None, xd.numel(), tag, float(np.float32(scale)),
+                                           int(zero_point), int(quant_min), int(quant_max), 0, _stream(xd.device))
+        _native.check(rc, "mctq_fq_affine_scalar")
+    return y
+
+
+def _affine_tensor_cuda(x, scale, zero_point, quant_min, quant_max):
+    tag = _dtype_tag(x)
+    _check_range(quant_min, quant_max)
+    if scale.numel() != 1 or zero_point.numel() != 1:
+        raise RuntimeError(f"a Tensor with {max(scale.numel(), zero_point.numel())} elements cannot be converted to Scalar")
+    if scale.dtype != torch.float32 or zero_point.dtype != torch.int32:
+        raise RuntimeError("scale must be Float and zero_point Int32")
+    xd = _dense(x)
+    y = torch.empty_like(xd)
+    if xd.numel():
+        lib = _native.load()
+        s, z = _param_on(scale, xd.device), _param_on(zero_point, xd.device)
+        with _on_device(xd.device):
+            rc = lib.mctq_fq_affine(_ptr(xd), _ptr(y), None, xd.numel(), tag, _ptr(s), _ptr(z), 1, 1, 0,
+                                    int(quant_min), int(quant_max), 0, _stream(xd.device))
+        _native.check(rc, "mctq_fq_affine")
+    return y
+
+
+def _affine_channel_launch(x, scale, zero_point, axis, quant_min, quant_max, code_mode, want_values):
+    tag = _dtype_tag(x)
+    _check_range(quant_min, quant_max)
+    _check_channel_params(x, scale, zero_point, axis)
+    xd, C, inner = _channel_layout(x, axis)
+    y = torch.empty_like(xd) if want_values else None
+    codes = None
+    n = xd.numel()
+    if code_mode == _native.CODES_INT8:
+        codes = torch.empty_like(xd, dtype=torch.int8 if quant_min < 0 else torch.uint8)
+    elif code_mode == _native.CODES_INT4:
+        codes = torch.empty((n + 1) // 2, dtype=torch.uint8, device=xd.device)
+    if n:
+        lib = _native.load()
+        s, z = _param_on(scale, xd.device), _param_on(zero_point, xd.device)
+        with _on_device(xd.device):
+            rc = lib.mctq_fq_affine(_ptr(xd), _ptr(y), _ptr(codes), n, tag, _ptr(s), _ptr(z), C, inner, 0,
+                                    int(quant_min), int(quant_max), int(code_mode), _stream(xd.device))
+        _native.check(rc, "mctq_fq_affine")
+    return y, codes
+
+
+def _affine_channel_cuda(x, scale, zero_point, axis, quant_min, quant_max):
+    return _affine_channel_launch(x, scale, zero_point, axis, quant_min, quant_max, 0, True)[0]
+
+
+def _quantize_affine_channel_cuda(x, scale, zero_point, axis, quant_min, quant_max, code_mode, want_values):
+    if code_mode not in (_native.CODES_INT8, _native.CODES_INT4):
+        raise RuntimeError("code_mode must be 1 (int8) or 2 (packed int4)")
+    y, codes = _affine_channel_launch(x, scale, zero_point, axis, quant_min, quant_max, code_mode, want_values)
+    if y is None:
+        y = torch.empty(0, dtype=x.dtype, device=x.device)
+    return codes, y
+
+
+def _dequantize_affine_cuda(codes, code_mode, is_signed, shape, scale, zero_point, axis):
+    n = 1
+    for s in shape:
+        n *= int(s)
+    nd = len(shape)
+    axis %= max(nd, 1)
+    C = int(shape[axis]) if nd else 1
+    inner = 1
+    for s in shape[axis + 1:]:
+        inner *= int(s)
+    if scale.numel() != C or zero_point.numel() != C:
+        raise RuntimeError("dimensions of scale and zero-point are not consistent with `shape`")
+    y = torch.empty(list(shape), dtype=torch.float32, device=codes.device)
+    if n:
+        lib = _native.load()
+        codes = codes.contiguous()
+        s, z = _param_on(scale, codes.device), _param_on(zero_point, codes.device)
+        with _on_device(codes.device):
+            rc = lib.mctq_dequant_affine(_ptr(codes), int(code_mode), int(bool(is_signed)), _ptr(y), n, _ptr(s), _ptr(z),
+                                         C, inner, 0, _stream(codes.device))
+        _native.check(rc, "mctq_dequant_affine")
+    return y
+
+
+def _lut_tensor_launch(x, table, K, threshold, per_channel, axis, eps, idx_mode, want_values):
+    tag = _dtype_tag(x)
+    if threshold.dtype != torch.float32:
+        raise RuntimeError(f"threshold must be Float, found {threshold.dtype}")
+    if per_channel:
+        if threshold.numel() != x.shape[axis]:
+            raise RuntimeError(f"shape '{[1] * x.dim()}' is invalid for threshold of size {threshold.numel()} "
+                               f"(input has {x.shape[axis]} channels on axis {axis})")
+        xd, C, inner = _channel_layout(x, axis)
+    else:
+        if threshold.numel() != 1:
+            raise RuntimeError("per-tensor LUT quantization needs a single threshold")
+        xd, C, inner = _dense(x), 1, 1
+    n = xd.numel()
+    y = torch.empty_like(xd, dtype=torch.float32) if want_values else None
+    idx = None
+    if idx_mode == _native.CODES_INT8:
+        idx = torch.empty_like(xd, dtype=torch.uint8)
+    elif idx_mode == _native.CODES_INT4:
+        idx = torch.empty((n + 1) // 2, dtype=torch.uint8, device=xd.device)
+    if n:
+        lib = _native.load()
+        t, thr = _param_on(table, xd.device), _param_on(threshold, xd.device)
+        with _on_device(xd.device):
+            rc = lib.mctq_fq_lut(_ptr(xd), _ptr(y), _ptr(idx), n, tag, _ptr(t), int(K), _ptr(thr), C, inner, 0,
+                                 float(np.float32(eps)), int(idx_mode), _stream(xd.device))
+        _native.check(rc, "mctq_fq_lut")
+    return y, idx
+
+
+def _lut_tensor_cuda(x, table, K, threshold, per_channel, axis, eps):
+    return _lut_tensor_launch(x, table, K, threshold, per_channel, axis, eps, 0, True)[0]
+
+
+def _lut_indices_cuda(x, table, K, threshold, per_channel, axis, eps, idx_mode):
+    if idx_mode not in (_native.CODES_INT8, _native.CODES_INT4):
+        raise RuntimeError("idx_mode must be 1 (uint8) or 2 (packed 4-bit)")
+    return _lut_tensor_launch(x, table, K, threshold, per_channel, axis, eps, idx_mode, False)[1]
+
+
+def _lut_scalar_cuda(x, table, K, divisor, threshold, round_to_input_dtype):
+    tag = _dtype_tag(x)
+    xd = _dense(x)
+    y = torch.empty_like(xd, dtype=torch.float32)
+    if xd.numel():
+        lib = _native.load()
+        t = _param_on(table, xd.device)
+        with _on_device(xd.device):
+            rc = lib.mctq_fq_lut_scalar(_ptr(xd), _ptr(y), None, xd.numel(), tag, _ptr(t), int(K),
+                                        float(np.float32(divisor)), float(np.float32(threshold)),
+                                        int(bool(round_to_input_dtype)), 0, _stream(xd.device))
+        _native.check(rc, "mctq_fq_lut_scalar")
+    return y
+
+
+# --------------------------------------------------------------------------------------------- CPU-tensor impls
+# A host tensor is streamed through the GPU in chunks (pinned memory overlaps copies and kernels).
+def _affine_host(x, scale_np, zp_np, C, inner, quant_min, quant_max):
+    dev = _require_cuda_for_host_path()
+    tag = _dtype_tag(x)
+    xc = x.contiguous()
+    y = torch.empty_like(xc, pin_memory=xc.is_pinned())
+    if xc.numel():
+        lib = _native.load()
+        stg = _staging_buffer(dev)
+        rc = lib.mctq_fq_affine_host(_ptr(xc), _ptr(y), xc.numel(), tag, scale_np.ctypes.data_as(c_vp),
+                                     zp_np.ctypes.data_as(c_vp), C, inner, int(quant_min), int(quant_max),
+                                     _ptr(stg), stg.numel(), dev)
+        _native.check(rc, "mctq_fq_affine_host")
+    return y
+
+
+def _affine_scalar_cpu(x, scale, zero_point, quant_min, quant_max):
+    _check_range(quant_min, quant_max)
+    if not quant_min <= zero_point <= quant_max:
+        raise RuntimeError("`zero_point` must be between `quant_min` and `quant_max`.")
+    return _affine_host(x, np.array([scale], dtype=np.float64).astype(np.float32), np.array([zero_point], dtype=np.int32),
+                        1, 1, quant_min, quant_max)
+
+
+def _affine_tensor_cpu(x, scale, zero_point, quant_min, quant_max):
+    _check_range(quant_min, quant_max)
+    if scale.numel() != 1 or zero_point.numel() != 1:
+        raise RuntimeError(f"a Tensor with {max(scale.numel(), zero_point.numel())} elements cannot be converted to Scalar")
+    return _affine_host(x, _host_array(scale, np.float32), _host_array(zero_point, np.int32), 1, 1, quant_min, quant_max)
+
+
+def _affine_channel_cpu(x, scale, zero_point, axis, quant_min, quant_max):
+    _check_range(quant_min, quant_max)
+    _check_channel_params(x, scale, zero_point, axis)
+    xc = x.contiguous()
+    _, C, inner = _channel_layout(xc, axis)
+    return _affine_host(xc, _host_array(scale, np.float32), _host_array(zero_point, np.int32), C, inner,
+                        quant_min, quant_max)
+
+
+def _lut_host(x, table, K, thr_np, C, inner, eps, scalar_mode, divisor, thr_f32, round_flag):
+    dev = _require_cuda_for_host_path()
+    tag = _dtype_tag(x)
+    xc = x.contiguous()
+    y = torch.empty(xc.shape, dtype=torch.float32, pin_memory=xc.is_pinned())
+    if xc.numel():
+        lib = _native.load()
+        stg = _staging_buffer(dev)
+        tab = table.detach().cpu().contiguous()
+        rc = lib.mctq_fq_lut_host(_ptr(xc), _ptr(y), xc.numel(), tag, _ptr(tab), int(K),
+                                  thr_np.ctypes.data_as(c_vp) if thr_np is not None else None, C, inner,
+                                  float(np.float32(eps)), int(scalar_mode), float(np.float32(divisor)),
+                                  float(np.float32(thr_f32)), int(round_flag), _ptr(stg), stg.numel(), dev)
+        _native.check(rc, "mctq_fq_lut_host")
+    return y
+
+
+def _lut_tensor_cpu(x, table, K, threshold, per_channel, axis, eps):
+    xc = x.contiguous()
+    if per_channel:
+        if threshold.numel() != xc.shape[axis]:
+            raise RuntimeError("threshold length does not match the channel axis")
+        _, C, inner = _channel_layout(xc, axis)
+    else:
+        C, inner = 1, 1
+    return _lut_host(xc, table, K, _host_array(threshold, np.float32), C, inner, eps, 0, 1.0, 1.0, 0)
+
+
+def _lut_scalar_cpu(x, table, K, divisor, threshold, round_to_input_dtype):
+    return _lut_host(x, table, K, None, 1, 1, 0.0, 1, divisor, threshold, round_to_input_dtype)
+
+
+def _no_host_path(name):
+    def impl(*args, **kwargs):
+        raise MctqError(f"mctq::{name} needs CUDA tensors (integer-code emission has no host-buffer entry point)")
+    return impl
+
+
+_LIB.impl("fq_affine_scalar", _affine_scalar_cuda, "CUDA")
+_LIB.impl("fq_affine_tensor", _affine_tensor_cuda, "CUDA")
+_LIB.impl("fq_affine_channel", _affine_channel_cuda, "CUDA")
+_LIB.impl("fq_lut_tensor", _lut_tensor_cuda, "CUDA")
+_LIB.impl("fq_lut_scalar", _lut_scalar_cuda, "CUDA")
+_LIB.impl("quantize_affine_channel", _quantize_affine_channel_cuda, "CUDA")
+_LIB.impl("dequantize_affine", _dequantize_affine_cuda, "CUDA")
+_LIB.impl("lut_indices", _lut_indices_cuda, "CUDA")
+
+_LIB.impl("fq_affine_scalar", _affine_scalar_cpu, "CPU")
+_LIB.impl("fq_affine_tensor", _affine_tensor_cpu, "CPU")
+_LIB.impl("fq_affine_channel", _affine_channel_cpu, "CPU")
+_LIB.impl("fq_lut_tensor", _lut_tensor_cpu, "CPU")
+_LIB.impl("fq_lut_scalar", _lut_scalar_cpu, "CPU")
+_LIB.impl("quantize_affine_channel", _no_host_path("quantize_affine_channel"), "CPU")
+_LIB.impl("dequantize_affine", _no_host_path("dequantize_affine"), "CPU")
+_LIB.impl("lut_indices", _no_host_path("lut_indices"), "CPU")
+
+
+# --------------------------------------------------------------------------------------------- fake / meta impls
+@torch.library.register_fake("mctq::fq_affine_scalar")
+def _(x, scale, zero_point, quant_min, quant_max):
+    return torch.empty_like(x)
+
+
+@torch.library.register_fake("mctq::fq_affine_tensor")
+def _(x, scale, zero_point, quant_min, quant_max):
+    return torch.empty_like(x)
+
+
+@torch.library.register_fake("mctq::fq_affine_channel")
+def _(x, scale, zero_point, axis, quant_min, quant_max):
+    return torch.empty_like(x)
+
+
+@torch.library.register_fake("mctq::fq_lut_tensor")
+def _(x, table, K, threshold, per_channel, axis, eps):
+    return torch.empty_like(x, dtype=torch.float32)
+
+
+@torch.library.register_fake("mctq::fq_lut_scalar")
+def _(x, table, K, divisor, threshold, round_to_input_dtype):
+    return torch.empty_like(x, dtype=torch.float32)
+
+
+@torch.library.register_fake("mctq::quantize_affine_channel")
+def _(x, scale, zero_point, axis, quant_min, quant_max, code_mode, want_values):
+    if code_mode == _native.CODES_INT4:
+        codes = x.new_empty(((x.numel() + 1) // 2,), dtype=torch.uint8)
+    else:
+        codes = torch.empty_like(x, dtype=torch.int8 if quant_min < 0 else torch.uint8)
+    return codes, (torch.empty_like(x) if want_values else x.new_empty((0,)))
+
+
+@torch.library.register_fake("mctq::dequantize_affine")
+def _(codes, code_mode, is_signed, shape, scale, zero_point, axis):
+    return codes.new_empty(list(shape), dtype=torch.float32)
+
+
+@torch.library.register_fake("mctq::lut_indices")
+def _(x, table, K, threshold, per_channel, axis, eps, idx_mode):
+    if idx_mode == _native.CODES_INT4:
+        return x.new_empty(((x.numel() + 1) // 2,), dtype=torch.uint8)
+    return torch.empty_like(x, dtype=torch.uint8)
+
+
+# --------------------------------------------------------------------------------------------- whole-model launch
+class MultiTensorPlan:
+    """One-launch fake-quant of many weight tensors (C ABI: mctq_fq_affine_multi).
+
+    Build once from [(x, scale, zp, axis, qmin, qmax)] (all CUDA, same device): outputs are allocated here and
+    reused by every run(); the descriptor table is uploaded once.  run() enqueues ONE kernel on the current
+    stream.  Reference loop being replaced: quantize_wrapper.py:228-240 / :260-270."""
+
+    def __init__(self, items):
+        lib = _native.load()
+        if not items:
+            raise ValueError("MultiTensorPlan needs at least one tensor")
+        self.device = items[0][0].device
+        self.inputs, self.outputs, self._keep = [], [], []
+        descs = (_native.MctqTensorDesc * len(items))()
+        for k, (x, scale, zp, axis, qmin, qmax) in enumerate(items):
+            if x.device != self.device or not x.is_cuda:
+                raise ValueError("all tensors of a MultiTensorPlan must live on one CUDA device")
+            _check_range(qmin, qmax)
+            if axis is None:
+                xd, C, inner = _dense(x), 1, 1
+                if scale.numel() != 1 or zp.numel() != 1:
+                    raise RuntimeError("per-tensor entry needs one scale / zero-point")
+            else:
+                _check_channel_params(x, scale, zp, axis)
+                xd, C, inner = _channel_layout(x, axis)
+            if xd.data_ptr() != x.data_ptr():
+                raise ValueError("MultiTensorPlan needs dense tensors (no hidden copies: the plan captures pointers)")
+            y = torch.empty_like(xd)
+            s, z = _param_on(scale.contiguous(), self.device), _param_on(zp.contiguous(), self.device)
+            self._keep += [s, z]
+            self.inputs.append(xd)
+            self.outputs.append(y)
+            d = descs[k]
+            d.x, d.y, d.codes, d.scale, d.zp = xd.data_ptr(), y.data_ptr(), None, s.data_ptr(), z.data_ptr()
+            d.n, d.C, d.inner = xd.numel(), C, inner
+            d.qmin, d.qmax, d.dtype, d.code_mode = int(qmin), int(qmax), _dtype_tag(xd), 0
+        starts = (ctypes.c_int32 * (len(items) + 1))()
+        total = lib.mctq_multi_plan(ctypes.cast(descs, c_vp), len(items), ctypes.cast(starts, c_vp))
+        if total < 0:
+            raise MctqError(f"mctq_multi_plan: {total}")
+        self.total_tiles = int(total)
+        self.n_desc = len(items)
+        self._descs_dev = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8).to(self.device)
+        self._starts_dev = torch.frombuffer(bytearray(bytes(starts)), dtype=torch.uint8).to(self.device)
+
+    def run(self):
+        lib = _native.load()
+        with _on_device(self.device):
+            rc = lib.mctq_fq_affine_multi(_ptr(self._descs_dev), _ptr(self._starts_dev), self.n_desc, self.total_tiles,
+                                          _stream(self.device))
+        _native.check(rc, "mctq_fq_affine_multi")
+        return self.outputs

@@ -1,0 +1,109 @@
+"""Host-side helpers of the PyTorch quantizers (reference: mct_quantizers/pytorch/quantizer_utils.py).
+
+`lut_quantizer` / `int_quantization_with_threshold` (reference :95-170) are NOT eager torch compositions
+here: they go through the `mctq` custom operators, i.e. the fused sm_100a LUT kernel.  Range fixing
+(`fix_range_to_include_zero`, reference :60-92) stays on the host -- it runs once per quantizer -- and is
+evaluated on CPU f32 tensors with exactly the reference's sequence of f32 operations so that derived scales
+and zero points are bit-identical.
+"""
+from typing import Tuple
+
+import numpy as np
+import torch
+
+from mct_quantizers_b200.logger import Logger
+
+
+def get_working_device():
+    """'cuda' (the current device) when a GPU is visible, else 'cpu' (reference :23-31)."""
+    return torch.device('cuda' if torch.cuda.is_available() else 'cpu')
+
+
+def to_torch_tensor(tensor):
+    """numpy / list / tuple / python scalar -> torch tensor on the working device (reference :34-57)."""
+    device = get_working_device()
+    if isinstance(tensor, torch.Tensor):
+        return tensor.to(device)
+    if isinstance(tensor, list):
+        return [to_torch_tensor(t) for t in tensor]
+    if isinstance(tensor, tuple):
+        return (to_torch_tensor(t) for t in tensor)
+    if isinstance(tensor, np.ndarray):
+        return torch.from_numpy(tensor.astype(np.float32)).to(device)
+    if isinstance(tensor, float):
+        return torch.Tensor([tensor]).to(device)
+    if isinstance(tensor, int):
+        return torch.Tensor([tensor]).int().to(device)
+    raise Exception(f'Conversion of type {type(tensor)} to {type(torch.Tensor)} is not supported')
+
+
+def fix_range_to_include_zero(range_min: torch.Tensor, range_max: torch.Tensor, n_bits: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Shift [min, max] so that 0.0 falls on the quantization grid (f32 tensor arithmetic, round-half-even).
+
+    Three cases per entry, selected with 0/1 masks exactly as the reference does (so that a strictly negative
+    range yields max = -0.0 just like it):  min > 0 -> (0, max);  max < 0 -> (min, 0);  otherwise the grid is
+    re-anchored at  step * round(min / step).  Note there is no final clamp (the numpy twin of the reference has
+    one; the torch path that the quantizers use does not)."""
+    lo_is_pos = range_min > 0
+    hi_is_neg = range_max < 0
+    straddles = torch.logical_and(torch.logical_not(lo_is_pos), torch.logical_not(hi_is_neg)).float()
+    lo_is_pos, hi_is_neg = lo_is_pos.float(), hi_is_neg.float()
+
+    step = (range_max - range_min) / (2 ** n_bits - 1)
+    lo_adj = step * torch.round(range_min / step)
+    hi_adj = range_max - range_min + lo_adj
+
+    lo_adj = lo_adj * straddles + hi_is_neg * range_min
+    hi_adj = hi_adj * straddles + lo_is_pos * range_max
+
+    span = range_max - range_min
+    if not torch.all(torch.isclose((lo_adj - range_min) / span, torch.tensor(0., device=span.device), atol=1e-6)):
+        Logger.warning(f"Adjusting (min_range, max_range) from ({range_min},{range_max}) to ({lo_adj},{hi_adj})")
+    return lo_adj, hi_adj
+
+
+_TABLE_CACHE = {}
+
+
+def lut_search_table(lut_values, lut_values_bitwidth: int, signed: bool) -> torch.Tensor:
+    """Centroid list -> search-table blob (uint8 CPU tensor) consumed by the LUT kernels; cached by content."""
+    from mct_quantizers_b200 import _native
+    key = (tuple(float(v) for v in np.asarray(lut_values, dtype=np.float32).reshape(-1)), int(lut_values_bitwidth), bool(signed))
+    tab = _TABLE_CACHE.get(key)
+    if tab is None:
+        blob = _native.build_lut_table(key[0], lut_values_bitwidth, signed)
+        tab = torch.frombuffer(bytearray(blob), dtype=torch.uint8)
+        _TABLE_CACHE[key] = tab
+    return tab
+
+
+def lut_quantizer(tensor_data: torch.Tensor,
+                  lut_values: torch.Tensor,
+                  signed: bool,
+                  threshold,
+                  lut_values_bitwidth: int,
+                  eps: float,
+                  per_channel: bool = None,
+                  channel_axis: int = None,
+                  input_rank: int = None,
+                  _table: torch.Tensor = None) -> torch.Tensor:
+    """Nearest-centroid fake-quant (same signature as the reference's lut_quantizer, :95-139):
+    normalise by (threshold + eps) into the 2^lut_values_bitwidth grid, clip, pick the first nearest LUT
+    entry, scale back by threshold.  `threshold` is an f32 tensor (weights) or a Python float (activations).
+    One fused kernel; f32 output."""
+    K = int(lut_values.numel())
+    table = _table if _table is not None else lut_search_table(lut_values.detach().cpu().numpy(), lut_values_bitwidth, signed)
+    if isinstance(threshold, torch.Tensor):
+        thr = threshold.reshape(-1)
+        if thr.dtype != torch.float32:
+            thr = thr.float()
+        if per_channel:
+            if input_rank is not None and input_rank != tensor_data.dim():
+                raise RuntimeError(f"input_rank is {input_rank} but the tensor has {tensor_data.dim()} dimensions")
+            return torch.ops.mctq.fq_lut_tensor(tensor_data, table, K, thr, True, int(channel_axis), float(eps))
+        return torch.ops.mctq.fq_lut_tensor(tensor_data, table, K, thr, False, 0, float(eps))
+    # Python-float threshold: the divisor is formed in double and narrowed once, and half-precision inputs keep
+    # their dtype through the normalisation (the reference's eager ops round after each step)
+    divisor = float(threshold) + float(eps)
+    return torch.ops.mctq.fq_lut_scalar(tensor_data, table, K, divisor, float(threshold),
+                                        tensor_data.dtype in (torch.bfloat16, torch.float16))

@@ -1,0 +1,439 @@
+"""Parity of the CUDA path (through the public quantizer API and through the raw C ABI) against
+  (a) the golden fixtures generated from the unmodified reference, and
+  (b) the CPU oracle (oracle/mctq_oracle.c) on seeded inputs, including ragged sizes, slices and large tensors.
+Bit-exact everywhere: f32 values, bf16/f16 values, integer codes and LUT indices.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import golden_util as G
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+CASES = G.case_names()
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def Q():
+    from mct_quantizers_b200.pytorch import quantizers
+    return quantizers
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from mct_quantizers_b200 import _native
+    return _native.load(build_if_missing=False)
+
+
+def _vp(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# ------------------------------------------------------------------------------------------- golden fixtures
+@pytest.mark.parametrize("name", CASES)
+def test_quantizer_matches_reference_fixture(name, Q):
+    """Public API on a CUDA tensor == output of the unmodified reference on CPU torch (bitwise)."""
+    case = G.get_case(name)
+    q = getattr(Q, case["cls"])(**case["args"])
+    x = G.to_torch(case["x"], case["x_dtype"], DEV)
+    y = q(x)
+    assert str(y.dtype).replace("torch.", "") == case["y_dtype"]
+    assert tuple(y.shape) == tuple(case["shape"])
+    got = G.from_torch(y)
+    assert G.bits_equal(got, case["y"]), G.mismatch_report(got, case["y"], case["x"])
+
+
+@pytest.mark.parametrize("name", [n for n in CASES if n.startswith(("wl_", "al_"))])
+def test_lut_indices_match_reference_fixture(name, lib):
+    """LUT index emission (uint8 and packed 4-bit) == argmin assignment re-derived with the reference's helper."""
+    from mct_quantizers_b200.pytorch.quantizer_utils import lut_search_table
+    case = G.get_case(name)
+    p = G.derive_params(case)
+    x = G.to_torch(case["x"], case["x_dtype"], DEV).contiguous()
+    n = x.numel()
+    table = lut_search_table(p["lut"], p["bw"], p["signed"]).to(DEV)
+    K = int(p["lut"].size)
+    want = case["idx"].reshape(-1)
+    for mode in (1, 2):
+        if mode == 2 and K > 16:
+            continue
+        idx = torch.full(((n if mode == 1 else (n + 1) // 2) + 8,), 0xEE, dtype=torch.uint8, device=DEV)
+        y = torch.empty(n, dtype=torch.float32, device=DEV)
+        if p["act"]:
+            d = np.float32(np.float64(p["thr"]) + np.float64(p["eps"]))
+            rc = lib.mctq_fq_lut_scalar(_vp(x), _vp(y), _vp(idx), n, G.DT_TAG[case["x_dtype"]], _vp(table), K, float(d),
+                                        float(np.float32(p["thr"])), int(case["x_dtype"] != "float32"), mode, _stream())
+        else:
+            thr = torch.from_numpy(p["thr"]).to(DEV)
+            rc = lib.mctq_fq_lut(_vp(x), _vp(y), _vp(idx), n, G.DT_TAG[case["x_dtype"]], _vp(table), K, _vp(thr), p["C"],
+                                 p["inner"], 0, float(np.float32(p["eps"])), mode, _stream())
+        assert rc == 0
+        torch.cuda.synchronize()
+        got = idx.cpu().numpy()
+        if mode == 1:
+            assert np.array_equal(got[:n].astype(np.int32), want)
+            assert (got[n:] == 0xEE).all()
+        else:
+            nb = (n + 1) // 2
+            lo, hi = got[:nb] & 0xF, got[:nb] >> 4
+            un = np.stack([lo, hi], 1).reshape(-1)[:n].astype(np.int32)
+            assert np.array_equal(un, want)
+            assert (got[nb:] == 0xEE).all()
+        assert G.bits_equal(y.cpu().numpy().reshape(case["y"].shape), case["y"])
+
+
+# ------------------------------------------------------------------------------------------- raw C ABI vs oracle
+def _rand_x(rng, n, dtype, scale=1.0):
+    v = (rng.standard_normal(n) * scale).astype(np.float32)
+    t = torch.from_numpy(v)
+    if dtype == "bfloat16":
+        t = t.bfloat16()
+    elif dtype == "float16":
+        t = t.half()
+    return t
+
+
+SIZES = [1, 3, 4, 5, 7, 8, 9, 31, 255, 1023, 1024, 1025, 4095, 4096, 4097, 8191, 8193, 16385, 100003]
+
+
+@pytest.mark.parametrize("dtype", ["float32", "bfloat16", "float16"])
+@pytest.mark.parametrize("code_mode", [0, 1, 2])
+def test_affine_ragged_sizes_and_codes(dtype, code_mode, lib):
+    """Every tail path of the tile kernel, per-tensor and per-channel, values + int8 / int4 codes vs the oracle."""
+    rng = np.random.default_rng(7)
+    tag = G.DT_TAG[dtype]
+    for n in SIZES:
+        for (C, inner) in [(1, 1), (3, 1), (5, 7), (4, 8), (2, 4096), (7, 1000)]:
+            if C * inner > n and C > 1 and n > 16:
+                pass
+            bits = 4 if code_mode == 2 else 8
+            signed = (n + C) % 2 == 0
+            qmin, qmax = (-(2 ** (bits - 1)), 2 ** (bits - 1) - 1) if signed else (0, 2 ** bits - 1)
+            scale = (np.abs(rng.standard_normal(C)) * 0.05 + 0.01).astype(np.float32)
+            zp = rng.integers(qmin, qmax + 1, size=C).astype(np.int32) if not signed else np.zeros(C, np.int32)
+            x = _rand_x(rng, n, dtype, 1.5)
+            xd = x.to(DEV)
+            y = torch.empty_like(xd)
+            ncode = n if code_mode == 1 else (n + 1) // 2
+            codes = torch.full((ncode + 8,), 0x5A, dtype=torch.uint8, device=DEV) if code_mode else None
+            rc = lib.mctq_fq_affine(_vp(xd), _vp(y), _vp(codes), n, tag, _vp(torch.from_numpy(scale).to(DEV)),
+                                    _vp(torch.from_numpy(zp).to(DEV)), C, inner, 0, qmin, qmax, code_mode, _stream())
+            assert rc == 0, (n, C, inner)
+            torch.cuda.synchronize()
+            want_y, want_codes = oracle.fq_affine(G.from_torch(x), tag, scale, zp, C, inner, qmin, qmax, want_codes=True)
+            got_y = G.from_torch(y)
+            assert G.bits_equal(got_y, want_y), (n, C, inner, G.mismatch_report(got_y, want_y))
+            if code_mode:
+                got = codes.cpu().numpy()
+                assert (got[ncode:] == 0x5A).all(), "wrote past the end of the code buffer"
+                if code_mode == 1:
+                    g = got[:n].view(np.int8).astype(np.int32) if signed else got[:n].astype(np.int32)
+                else:
+                    nib = np.stack([got[:ncode] & 0xF, got[:ncode] >> 4], 1).reshape(-1)[:n].astype(np.int32)
+                    g = np.where(nib >= 8, nib - 16, nib) if signed else nib
+                    if n % 2:
+                        assert got[ncode - 1] >> 4 == 0
+                assert np.array_equal(g, want_codes), (n, C, inner)
+
+
+@pytest.mark.parametrize("dtype", ["float32", "bfloat16"])
+def test_affine_elem_offset_slices(dtype, lib):
+    """A tensor processed as arbitrary flat slices (elem_offset) == processed whole: the contract behind
+    batch / channel-block sharding and host staging."""
+    rng = np.random.default_rng(11)
+    tag = G.DT_TAG[dtype]
+    outer, C, inner = 3, 37, 53
+    n = outer * C * inner
+    scale = (np.abs(rng.standard_normal(C)) * 0.02 + 0.005).astype(np.float32)
+    zp = rng.integers(0, 256, size=C).astype(np.int32)
+    x = _rand_x(rng, n, dtype, 2.0)
+    want = oracle.fq_affine(G.from_torch(x), tag, scale, zp, C, inner, 0, 255)
+    sd, zd = torch.from_numpy(scale).to(DEV), torch.from_numpy(zp).to(DEV)
+    cuts = sorted(set([0, n] + [int(c) for c in rng.integers(1, n, size=9)] + [8 * int(c) for c in rng.integers(1, n // 8, size=4)]))
+    got = np.empty_like(want)
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        xs = x[a:b].clone().to(DEV)          # fresh (aligned) allocation holding the slice
+        ys = torch.empty_like(xs)
+        assert lib.mctq_fq_affine(_vp(xs), _vp(ys), None, b - a, tag, _vp(sd), _vp(zd), C, inner, a, 0, 255, 0, _stream()) == 0
+        got[a:b] = G.from_torch(ys)
+    assert G.bits_equal(got, want)
+    # misaligned views (odd element offsets) take the scalar fallback kernel
+    xd = x.to(DEV)
+    for a in (1, 3, 5):
+        ys = torch.empty(n - a + 1, dtype=xd.dtype, device=DEV)[1:]
+        assert lib.mctq_fq_affine(_vp(xd[a:]), _vp(ys), None, n - a, tag, _vp(sd), _vp(zd), C, inner, a, 0, 255, 0, _stream()) == 0
+        assert G.bits_equal(G.from_torch(ys), want[a:])
+
+
+@pytest.mark.parametrize("dtype", ["float32", "bfloat16", "float16"])
+def test_lut_ragged_sizes(dtype, lib):
+    from mct_quantizers_b200.pytorch.quantizer_utils import lut_search_table
+    rng = np.random.default_rng(5)
+    tag = G.DT_TAG[dtype]
+    lut = np.array(sorted(rng.choice(np.arange(-128, 128), size=16, replace=False)), dtype=np.float32)
+    table = lut_search_table(lut, 8, True).to(DEV)
+    for n in SIZES:
+        for (C, inner) in [(1, 1), (3, 1), (5, 7), (4, 8), (2, 4096), (6, 1000)]:
+            thr = (np.abs(rng.standard_normal(C)) + 0.05).astype(np.float32)
+            x = _rand_x(rng, n, dtype, 0.6)
+            xd = x.to(DEV)
+            y = torch.empty(n, dtype=torch.float32, device=DEV)
+            rc = lib.mctq_fq_lut(_vp(xd), _vp(y), None, n, tag, _vp(table), 16, _vp(torch.from_numpy(thr).to(DEV)), C, inner, 0,
+                                 float(np.float32(1e-8)), 0, _stream())
+            assert rc == 0
+            torch.cuda.synchronize()
+            want = oracle.fq_lut(G.from_torch(x), tag, lut, thr, C, inner, 8, True, 1e-8)
+            assert G.bits_equal(y.cpu().numpy(), want), (n, C, inner, G.mismatch_report(y.cpu().numpy(), want))
+
+
+def test_lut_all_table_sizes_and_ieee_variant(lib):
+    """K = 1 .. 256 centroids (every padded search depth), fast division vs the IEEE-division variant."""
+    from mct_quantizers_b200.pytorch.quantizer_utils import lut_search_table
+    rng = np.random.default_rng(9)
+    n = 50000
+    x = _rand_x(rng, n, "float32", 0.5)
+    xd = x.to(DEV)
+    thr = np.array([0.9, 0.013, 2.0], dtype=np.float32)
+    for K in (1, 2, 3, 5, 16, 17, 64, 100, 256):
+        lut = rng.choice(np.arange(-128, 128), size=K, replace=False).astype(np.float32)   # unsorted on purpose
+        table = lut_search_table(lut, 8, True).to(DEV)
+        want, want_idx = oracle.fq_lut(x.numpy(), oracle.F32, lut, thr, 3, 5, 8, True, 1e-8, want_idx=True)
+        for ieee in (0, 1):
+            lib.mctq_set_tuning(2, ieee)
+            y = torch.empty(n, dtype=torch.float32, device=DEV)
+            idx = torch.empty(n, dtype=torch.uint8, device=DEV)
+            rc = lib.mctq_fq_lut(_vp(xd), _vp(y), _vp(idx) if not ieee else None, n, 0, _vp(table), K,
+                                 _vp(torch.from_numpy(thr).to(DEV)), 3, 5, 0, float(np.float32(1e-8)), 0 if ieee else 1, _stream())
+            lib.mctq_set_tuning(2, 0)
+            assert rc == 0
+            assert G.bits_equal(y.cpu().numpy(), want), (K, ieee)
+            if not ieee:
+                assert np.array_equal(idx.cpu().numpy().astype(np.int32), want_idx)
+
+
+def test_division_selftest(lib):
+    """The 5-operation correctly-rounded division of the LUT kernels == __fdiv_rn on 2^31 (x, d) pairs."""
+    bad = torch.zeros(1, dtype=torch.int64, device=DEV)
+    assert lib.mctq_selftest_division(1 << 31, 0x1234, _vp(bad), _stream()) == 0
+    torch.cuda.synchronize()
+    assert int(bad.item()) == 0
+
+
+def test_rint_variant_and_wide_ranges(lib):
+    """16-bit and 24-bit ranges; the rint-based variant (forced, and auto-selected beyond 2^21) == oracle."""
+    rng = np.random.default_rng(3)
+    n = 70001
+    x = _rand_x(rng, n, "float32", 3.0)
+    xd = x.to(DEV)
+    for bits, force in ((8, 1), (16, 0), (16, 1), (24, 0)):
+        qmin, qmax = -(2 ** (bits - 1)), 2 ** (bits - 1) - 1
+        scale = np.array([8.0 / 2 ** (bits - 1)], dtype=np.float32)
+        zp = np.zeros(1, np.int32)
+        lib.mctq_set_tuning(1, force)
+        y = torch.empty_like(xd)
+        rc = lib.mctq_fq_affine_scalar(_vp(xd), _vp(y), None, n, 0, float(scale[0]), 0, qmin, qmax, 0, _stream())
+        lib.mctq_set_tuning(1, 0)
+        assert rc == 0
+        want = oracle.fq_affine(x.numpy(), 0, scale, zp, 1, 1, qmin, qmax)
+        assert G.bits_equal(y.cpu().numpy(), want), (bits, force)
+
+
+def test_unroll_variants_agree(lib):
+    rng = np.random.default_rng(4)
+    n = 1 << 20
+    for dtype in ("float32", "bfloat16"):
+        x = _rand_x(rng, n + 13, dtype, 2.0).to(DEV)
+        outs = []
+        for u in (2, 4, 8):
+            lib.mctq_set_tuning(0, u)
+            y = torch.empty_like(x)
+            assert lib.mctq_fq_affine_scalar(_vp(x), _vp(y), None, x.numel(), G.DT_TAG[dtype], 0.03125, 0, -128, 127, 0, _stream()) == 0
+            outs.append(y)
+        lib.mctq_set_tuning(0, 4)
+        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
+
+
+def test_dequant_roundtrip(lib):
+    """codes -> mctq_dequant_affine == fake-quant values (f32), int8 and packed int4, signed and unsigned."""
+    rng = np.random.default_rng(12)
+    C, inner, outer = 11, 24, 5
+    n = C * inner * outer
+    x = _rand_x(rng, n, "float32", 1.0).to(DEV)
+    for bits, signed, mode in ((8, True, 1), (8, False, 1), (4, True, 2), (4, False, 2)):
+        qmin, qmax = (-(2 ** (bits - 1)), 2 ** (bits - 1) - 1) if signed else (0, 2 ** bits - 1)
+        scale = torch.from_numpy((np.abs(rng.standard_normal(C)) * 0.1 + 0.01).astype(np.float32)).to(DEV)
+        zp = torch.from_numpy((np.zeros(C) if signed else rng.integers(0, qmax + 1, size=C)).astype(np.int32)).to(DEV)
+        y = torch.empty_like(x)
+        codes = torch.empty(n if mode == 1 else (n + 1) // 2, dtype=torch.uint8, device=DEV)
+        assert lib.mctq_fq_affine(_vp(x), _vp(y), _vp(codes), n, 0, _vp(scale), _vp(zp), C, inner, 0, qmin, qmax, mode, _stream()) == 0
+        back = torch.empty_like(x)
+        assert lib.mctq_dequant_affine(_vp(codes), mode, int(signed), _vp(back), n, _vp(scale), _vp(zp), C, inner, 0, _stream()) == 0
+        assert torch.equal(back.view(torch.int32), y.view(torch.int32))
+        # codes-only mode (y == NULL)
+        codes2 = torch.empty_like(codes)
+        assert lib.mctq_fq_affine(_vp(x), None, _vp(codes2), n, 0, _vp(scale), _vp(zp), C, inner, 0, qmin, qmax, mode, _stream()) == 0
+        assert torch.equal(codes, codes2)
+
+
+def test_bad_arguments(lib):
+    x = torch.zeros(16, device=DEV)
+    y = torch.empty_like(x)
+    s = torch.ones(1, device=DEV)
+    z = torch.zeros(1, dtype=torch.int32, device=DEV)
+    assert lib.mctq_fq_affine(_vp(x), _vp(y), None, 16, 7, _vp(s), _vp(z), 1, 1, 0, 0, 255, 0, None) == -2     # dtype
+    assert lib.mctq_fq_affine(_vp(x), _vp(y), None, 16, 0, _vp(s), _vp(z), 1, 1, 0, 5, 2, 0, None) == -3       # qmin > qmax
+    assert lib.mctq_fq_affine(_vp(x), _vp(y), None, -1, 0, _vp(s), _vp(z), 1, 1, 0, 0, 255, 0, None) == -1
+    assert lib.mctq_fq_affine(_vp(x), _vp(y), _vp(y), 16, 0, _vp(s), _vp(z), 1, 1, 0, 0, 1023, 1, None) == -3  # codes do not fit
+    assert lib.mctq_fq_affine(_vp(x), _vp(y), None, 0, 0, _vp(s), _vp(z), 1, 1, 0, 0, 255, 0, None) == 0       # empty is fine
+    torch.cuda.synchronize()
+
+
+# ------------------------------------------------------------------------------------------- large tensors
+def test_large_tensor_properties(Q):
+    """BASELINE-scale tensors: oracle on sampled windows + size-independent properties (idempotence, code
+    range, checksum agreement between two independent launches)."""
+    g = torch.Generator(device=DEV).manual_seed(1234)
+    n = (1 << 28) + 12345                                        # 1 GiB of f32 (+ ragged tail)
+    x = torch.empty(n, device=DEV).uniform_(-50, 50, generator=g)
+    q = Q.ActivationSymmetricInferableQuantizer(8, [4.0], True)
+    y = q(x)
+    y2 = q(y)
+    assert torch.equal(y.view(torch.int32), y2.view(torch.int32))            # idempotent
+    codes = torch.round(y / (4.0 / 128))
+    assert codes.min().item() >= -128 and codes.max().item() <= 127
+    scale = np.array([4.0 / 128], dtype=np.float32)
+    for start in (0, 4096 * 777 + 3, n - 100000):
+        xs = x[start:start + 100000].cpu().numpy()
+        want = oracle.fq_affine(xs, 0, scale, np.zeros(1, np.int32), 1, 1, -128, 127)
+        assert G.bits_equal(y[start:start + 100000].cpu().numpy(), want)
+    del y2, codes
+    # per-channel on a Llama-shaped matrix, bf16, channel axis 0 and 1
+    W = torch.empty(4096, 11008, device=DEV).normal_(0, 0.02, generator=g).bfloat16()
+    for axis in (0, 1):
+        thr = W.float().abs().amax(dim=1 - axis).cpu().numpy().astype(np.float64)
+        qw = Q.WeightsSymmetricInferableQuantizer(8, [float(t) for t in thr], True, axis)
+        yw = qw(W)
+        rows = slice(1000, 1016)
+        C, inner = (4096, 11008) if axis == 0 else (11008, 1)
+        sub = W[rows].contiguous()
+        sc = (thr / 128).astype(np.float32)
+        if axis == 0:
+            want = oracle.fq_affine(G.from_torch(sub), oracle.BF16, sc[rows], np.zeros(16, np.int32), 16, inner, -128, 127)
+        else:
+            want = oracle.fq_affine(G.from_torch(sub), oracle.BF16, sc, np.zeros(C, np.int32), C, 1, -128, 127)
+        assert G.bits_equal(G.from_torch(yw[rows]), want)
+
+
+def test_index_space_beyond_32_bits(lib):
+    """More than 2^32 bytes and more than 2^31 elements in one call (bf16): tail of the tensor is correct."""
+    n = (1 << 31) + (1 << 20) + 7
+    x = torch.empty(n, dtype=torch.bfloat16, device=DEV)
+    x[:1 << 20].normal_(0, 2)
+    x[-(1 << 20):].normal_(0, 2)
+    y = torch.empty_like(x)
+    C, inner = 3, 1 << 29
+    scale = torch.tensor([0.05, 0.01, 0.2], device=DEV)
+    zp = torch.zeros(3, dtype=torch.int32, device=DEV)
+    assert lib.mctq_fq_affine(_vp(x), _vp(y), None, n, 1, _vp(scale), _vp(zp), C, inner, 0, -128, 127, 0, _stream()) == 0
+    torch.cuda.synchronize()
+    tail = 1 << 20
+    # channel of element i is (i / 2^29) % 3: the tail starts in row 4 (channel 1)
+    i0 = n - tail
+    ch = ((np.arange(i0, n, dtype=np.int64) // inner) % C)
+    sc = scale.cpu().numpy()
+    xt = G.from_torch(x[-tail:])
+    want = np.empty(tail, dtype=np.uint16)
+    for c in range(3):
+        m = ch == c
+        if m.any():
+            want[m] = oracle.fq_affine(xt[m], oracle.BF16, sc[c:c + 1], np.zeros(1, np.int32), 1, 1, -128, 127)
+    assert G.bits_equal(G.from_torch(y[-tail:]), want)
+    xh = G.from_torch(x[:tail])
+    want_h = oracle.fq_affine(xh, oracle.BF16, sc[0:1], np.zeros(1, np.int32), 1, 1, -128, 127)
+    assert G.bits_equal(G.from_torch(y[:tail]), want_h)
+
+
+# ------------------------------------------------------------------------------------------- layouts, host path, multi
+def test_dense_permuted_layouts_keep_strides(Q):
+    rng = np.random.default_rng(21)
+    x = torch.from_numpy(rng.standard_normal((4, 6, 5, 7)).astype(np.float32)).to(DEV)
+    thr = [float(v) for v in np.abs(rng.standard_normal(6)) + 0.1]
+    q = Q.WeightsSymmetricInferableQuantizer(4, thr, True, 1)
+    ref = q(x.clone())
+    xcl = x.clone().contiguous(memory_format=torch.channels_last)
+    ycl = q(xcl)
+    assert ycl.stride() == xcl.stride()
+    assert torch.equal(ycl, ref)
+    xt = x.clone().permute(3, 1, 0, 2)                     # arbitrary dense permutation, channel axis now 1
+    yt = q(xt)
+    assert torch.equal(yt, ref.permute(3, 1, 0, 2))
+    xs = x.clone()[:, :, ::2]                               # genuinely strided: falls back to a contiguous copy
+    assert torch.equal(q(xs), ref[:, :, ::2])
+    a = Q.ActivationUniformInferableQuantizer(8, [-1.0], [2.3])
+    assert torch.equal(a(xcl), a(x))
+    assert a(xcl).stride() == xcl.stride()
+
+
+@pytest.mark.parametrize("name", ["w_sym_b8_pc_6x5x3x3_ax0", "w_uni_b4_pc_4x7x3x5_ax1", "a_uni_b8_straddle", "a_sym_b8_s_bfloat16_allbits",
+                                  "wl_sym_lut16_pc_6x40_ax0", "al_s_l16_t4.0", "al_u_t0.0625_float16_allbits", "w_pot_b8_pt"])
+def test_host_tensor_path_matches_reference_fixture(name, Q):
+    """CPU tensors are streamed through the GPU (mctq_fq_*_host): same bits, result lands in host memory."""
+    case = G.get_case(name)
+    q = getattr(Q, case["cls"])(**case["args"])
+    x = G.to_torch(case["x"], case["x_dtype"], "cpu")
+    y = q(x)
+    assert y.device.type == "cpu"
+    assert G.bits_equal(G.from_torch(y), case["y"])
+    y = q(x.pin_memory())
+    assert G.bits_equal(G.from_torch(y), case["y"])
+
+
+def test_host_path_multi_chunk(Q):
+    """A host tensor larger than several staging chunks (per-channel, ragged rows) == device path."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.empty(37, 1 << 20, dtype=torch.float32).normal_(0, 1, generator=g)       # 155 MB, rows not chunk aligned
+    thr = [0.5 + 0.1 * i for i in range(37)]
+    q = Q.WeightsSymmetricInferableQuantizer(8, thr, True, 0)
+    y_host = q(x.clone())
+    y_dev = q(x.clone().to(DEV))
+    assert torch.equal(y_host, y_dev.cpu())
+    ql = Q.WeightsLUTSymmetricInferableQuantizer(4, [float(v) for v in range(-128, 128, 16)], thr, True, 0, 2)
+    assert torch.equal(ql(x.clone()), ql(x.clone().to(DEV)).cpu())
+
+
+def test_whole_model_single_launch(Q, lib):
+    """quantize_model_weights: every affine weight quantizer of a model in ONE kernel == per-layer calls."""
+    import mct_quantizers_b200 as mctq
+    torch.manual_seed(0)
+    layers = [torch.nn.Conv2d(3, 16, 3), torch.nn.Conv2d(16, 32, 3, groups=16), torch.nn.Conv2d(32, 8, 1),
+              torch.nn.Linear(40, 10)]
+    wrapped = []
+    for i, layer in enumerate(layers):
+        w = layer.weight.detach()
+        C = w.shape[0]
+        if i % 2 == 0:
+            thr = [float(v) for v in w.abs().flatten(1).amax(1)]
+            qz = Q.WeightsSymmetricInferableQuantizer(8, thr, True, 0)
+        else:
+            lo = [float(v) for v in w.flatten(1).amin(1) - 0.01]
+            hi = [float(v) for v in w.flatten(1).amax(1) + 0.01]
+            qz = Q.WeightsUniformInferableQuantizer(8, lo, hi, True, 0)
+        wrapped.append(mctq.PytorchQuantizationWrapper(layer, {'weight': qz}))
+    model = torch.nn.Sequential(*wrapped).to(DEV)
+    before = lib.mctq_launch_count()
+    fused = mctq.quantize_model_weights(model)
+    assert lib.mctq_launch_count() - before == 1
+    for name, mod in model.named_children():
+        per_layer = mod.get_quantized_weights()
+        assert torch.equal(per_layer['weight'], fused[name]['weight'])
+    for mod in model.children():
+        assert mod.quantize_weights_batched().keys() == {'weight'}
