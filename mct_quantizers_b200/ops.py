@@ -71,11 +71,22 @@ class _on_device:
             torch.cuda.set_device(self.prev)
 
 
+def _is_dense_permutation(x):
+    """True when x's elements occupy one gap-free block of memory in some permutation of its dims."""
+    dims = sorted((d for d in range(x.dim()) if x.shape[d] > 1), key=lambda d: x.stride(d))
+    expect = 1
+    for d in dims:
+        if x.stride(d) != expect:
+            return False
+        expect *= x.shape[d]
+    return True
+
+
 def _dense(x):
     """x itself when its memory is one dense block (any permutation of strides), else a contiguous copy."""
     if x.is_contiguous() or x.numel() == 0:
         return x
-    if x.is_non_overlapping_and_dense():
+    if _is_dense_permutation(x):
         return x
     return x.contiguous()
 

@@ -125,8 +125,9 @@ def test_affine_ragged_sizes_and_codes(dtype, code_mode, lib):
             y = torch.empty_like(xd)
             ncode = n if code_mode == 1 else (n + 1) // 2
             codes = torch.full((ncode + 8,), 0x5A, dtype=torch.uint8, device=DEV) if code_mode else None
-            rc = lib.mctq_fq_affine(_vp(xd), _vp(y), _vp(codes), n, tag, _vp(torch.from_numpy(scale).to(DEV)),
-                                    _vp(torch.from_numpy(zp).to(DEV)), C, inner, 0, qmin, qmax, code_mode, _stream())
+            sd, zd = torch.from_numpy(scale).to(DEV), torch.from_numpy(zp).to(DEV)     # keep alive across the launch
+            rc = lib.mctq_fq_affine(_vp(xd), _vp(y), _vp(codes), n, tag, _vp(sd), _vp(zd), C, inner, 0, qmin, qmax,
+                                    code_mode, _stream())
             assert rc == 0, (n, C, inner)
             torch.cuda.synchronize()
             want_y, want_codes = oracle.fq_affine(G.from_torch(x), tag, scale, zp, C, inner, qmin, qmax, want_codes=True)
@@ -187,7 +188,8 @@ def test_lut_ragged_sizes(dtype, lib):
             x = _rand_x(rng, n, dtype, 0.6)
             xd = x.to(DEV)
             y = torch.empty(n, dtype=torch.float32, device=DEV)
-            rc = lib.mctq_fq_lut(_vp(xd), _vp(y), None, n, tag, _vp(table), 16, _vp(torch.from_numpy(thr).to(DEV)), C, inner, 0,
+            td = torch.from_numpy(thr).to(DEV)
+            rc = lib.mctq_fq_lut(_vp(xd), _vp(y), None, n, tag, _vp(table), 16, _vp(td), C, inner, 0,
                                  float(np.float32(1e-8)), 0, _stream())
             assert rc == 0
             torch.cuda.synchronize()
@@ -203,6 +205,7 @@ def test_lut_all_table_sizes_and_ieee_variant(lib):
     x = _rand_x(rng, n, "float32", 0.5)
     xd = x.to(DEV)
     thr = np.array([0.9, 0.013, 2.0], dtype=np.float32)
+    td = torch.from_numpy(thr).to(DEV)
     for K in (1, 2, 3, 5, 16, 17, 64, 100, 256):
         lut = rng.choice(np.arange(-128, 128), size=K, replace=False).astype(np.float32)   # unsorted on purpose
         table = lut_search_table(lut, 8, True).to(DEV)
@@ -212,7 +215,7 @@ def test_lut_all_table_sizes_and_ieee_variant(lib):
             y = torch.empty(n, dtype=torch.float32, device=DEV)
             idx = torch.empty(n, dtype=torch.uint8, device=DEV)
             rc = lib.mctq_fq_lut(_vp(xd), _vp(y), _vp(idx) if not ieee else None, n, 0, _vp(table), K,
-                                 _vp(torch.from_numpy(thr).to(DEV)), 3, 5, 0, float(np.float32(1e-8)), 0 if ieee else 1, _stream())
+                                 _vp(td), 3, 5, 0, float(np.float32(1e-8)), 0 if ieee else 1, _stream())
             lib.mctq_set_tuning(2, 0)
             assert rc == 0
             assert G.bits_equal(y.cpu().numpy(), want), (K, ieee)

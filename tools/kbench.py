@@ -1,0 +1,141 @@
+#!/usr/bin/env python
+"""Kernel micro-benchmark (GPU box): achieved algorithmic GB/s of each kernel family through the raw C ABI.
+CUDA events on the launch stream, buffers rotated so that nothing is L2-resident, median of reps.
+
+    python tools/kbench.py [--mb 1024] [--reps 20] [--what affine,lut,codes] [--unroll 2,4,8]
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mct_quantizers_b200 import _native  # noqa: E402
+from mct_quantizers_b200.pytorch.quantizer_utils import lut_search_table  # noqa: E402
+
+DT = {"f32": (torch.float32, 0, 4), "bf16": (torch.bfloat16, 1, 2), "f16": (torch.float16, 2, 2)}
+
+
+def vp(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def timeit(fn, reps, nbuf):
+    st = torch.cuda.current_stream()
+    for i in range(3):
+        fn(i % nbuf)
+    torch.cuda.synchronize()
+    ts = []
+    for i in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(st)
+        fn(i % nbuf)
+        b.record(st)
+        b.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--mb", type=float, default=1024.0, help="input megabytes per launch")
+    ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--what", default="affine,channel,codes,lut,copy")
+    ap.add_argument("--unroll", default="4")
+    ap.add_argument("--dtypes", default="f32,bf16")
+    ap.add_argument("--json", default=None)
+    args = ap.parse_args()
+    lib = _native.load(build_if_missing=False)
+    dev = torch.device("cuda:0")
+    stream = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)  # noqa: E731
+    peak = 6457.7
+    try:
+        peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    rows = []
+    what = args.what.split(",")
+    nbuf = 3
+
+    def report(name, dt, algo_bytes, med, best):
+        gbs = algo_bytes / med / 1e6
+        rows.append({"kernel": name, "dtype": dt, "mb_in": args.mb, "median_ms": round(med, 4), "best_ms": round(best, 4),
+                     "GBs": round(gbs, 1), "frac_of_copy_peak": round(gbs / peak, 4), "pct_of_8TBs": round(gbs / 80.0, 2)})
+        print(f"{name:46s} {dt:5s} {args.mb:8.0f} MB  median {med:8.4f} ms  {gbs:8.1f} GB/s  {gbs / peak * 100:6.2f}% of copy peak "
+              f"{gbs / 80:6.2f}% of 8TB/s", flush=True)
+
+    for dt in args.dtypes.split(","):
+        tdt, tag, es = DT[dt]
+        n = int(args.mb * 1e6 / es) // 4096 * 4096
+        xs = [torch.empty(n, dtype=tdt, device=dev).uniform_(-50, 50) for _ in range(nbuf)]
+        ys = [torch.empty(n, dtype=tdt, device=dev) for _ in range(nbuf)]
+        if "copy" in what:
+            med, best = timeit(lambda i: ys[i].copy_(xs[i]), args.reps, nbuf)
+            report("torch copy_ (reference point)", dt, 2 * n * es, med, best)
+        for u in [int(v) for v in args.unroll.split(",")]:
+            lib.mctq_set_tuning(0, u)
+            if "affine" in what:
+                med, best = timeit(lambda i: lib.mctq_fq_affine_scalar(vp(xs[i]), vp(ys[i]), None, n, tag, 0.03125, 0, -128, 127, 0, stream()),
+                                   args.reps, nbuf)
+                report(f"affine per-tensor scalar u{u}", dt, 2 * n * es, med, best)
+                med, best = timeit(lambda i: lib.mctq_fq_affine_scalar(vp(xs[i]), vp(ys[i]), None, n, tag, 0.0129, 77, 0, 255, 0, stream()),
+                                   args.reps, nbuf)
+                report(f"affine per-tensor uniform zp u{u}", dt, 2 * n * es, med, best)
+            if "channel" in what:
+                for (C, inner, label) in ((4096, 11008, "rows 11008"), (11008, 4096, "rows 4096"), (512, 4608, "conv 512x512x3x3"),
+                                          (960, 9, "depthwise inner 9"), (768, 1, "channel-last C=768"), (3, 1, "channel-last C=3")):
+                    sc = torch.rand(C, device=dev) * 0.05 + 0.01
+                    zp = torch.zeros(C, dtype=torch.int32, device=dev)
+                    med, best = timeit(lambda i: lib.mctq_fq_affine(vp(xs[i]), vp(ys[i]), None, n, tag, vp(sc), vp(zp), C, inner, 0, -128, 127, 0, stream()),
+                                       args.reps, nbuf)
+                    report(f"affine per-channel {label} u{u}", dt, 2 * n * es, med, best)
+        lib.mctq_set_tuning(0, 4)
+        if "codes" in what:
+            cs = [torch.empty(n, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
+            med, best = timeit(lambda i: lib.mctq_fq_affine_scalar(vp(xs[i]), vp(ys[i]), vp(cs[i]), n, tag, 0.03125, 0, -128, 127, 1, stream()), args.reps, nbuf)
+            report("affine per-tensor + int8 codes", dt, n * (2 * es + 1), med, best)
+            med, best = timeit(lambda i: lib.mctq_fq_affine_scalar(vp(xs[i]), None, vp(cs[i]), n, tag, 0.03125, 0, -128, 127, 1, stream()), args.reps, nbuf)
+            report("affine per-tensor int8 codes only", dt, n * (es + 1), med, best)
+            med, best = timeit(lambda i: lib.mctq_fq_affine_scalar(vp(xs[i]), vp(ys[i]), vp(cs[i]), n, tag, 0.5, 0, -8, 7, 2, stream()), args.reps, nbuf)
+            report("affine per-tensor + int4 codes", dt, n * (2 * es + 0.5), med, best)
+            del cs
+        if "lut" in what:
+            del ys
+            yf = [torch.empty(n, dtype=torch.float32, device=dev) for _ in range(nbuf)]
+            rng = np.random.default_rng(0)
+            lut = np.array(sorted(rng.choice(np.arange(-128, 128), size=16, replace=False)), dtype=np.float32)
+            table = lut_search_table(lut, 8, True).to(dev)
+            for x in xs:
+                x.normal_(0, 0.02)
+            for u in [int(v) for v in args.unroll.split(",") if int(v) in (4, 8)] or [4]:
+                lib.mctq_set_tuning(0, u)
+                for (C, inner, label) in ((4096, 11008, "rows 11008"), (11008, 4096, "rows 4096"), (1, 1, "per-tensor")):
+                    thr = torch.rand(C, device=dev) * 0.05 + 0.06
+                    med, best = timeit(lambda i: lib.mctq_fq_lut(vp(xs[i]), vp(yf[i]), None, n, tag, vp(table), 16, vp(thr), C, inner, 0,
+                                                                 1e-8, 0, stream()), args.reps, nbuf)
+                    report(f"lut K=16 weights {label} u{u}", dt, n * (es + 4), med, best)
+                med, best = timeit(lambda i: lib.mctq_fq_lut_scalar(vp(xs[i]), vp(yf[i]), None, n, tag, vp(table), 16, 0.125, 0.125, int(es == 2), 0, stream()),
+                                   args.reps, nbuf)
+                report(f"lut K=16 activation scalar u{u}", dt, n * (es + 4), med, best)
+            lib.mctq_set_tuning(0, 4)
+            lib.mctq_set_tuning(2, 1)
+            thr = torch.rand(4096, device=dev) * 0.05 + 0.06
+            med, best = timeit(lambda i: lib.mctq_fq_lut(vp(xs[i]), vp(yf[i]), None, n, tag, vp(table), 16, vp(thr), 4096, 11008, 0, 1e-8, 0, stream()),
+                               args.reps, nbuf)
+            report("lut K=16 weights rows 11008 IEEE-div variant", dt, n * (es + 4), med, best)
+            lib.mctq_set_tuning(2, 0)
+            del yf
+        del xs
+        torch.cuda.empty_cache()
+    if args.json:
+        with open(args.json, "w") as f:
+            json.dump({"peak_gbs": peak, "rows": rows}, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
