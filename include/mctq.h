@@ -152,6 +152,28 @@ int mctq_fq_lut_scalar(const void* x, float* y, void* idx, int64_t n, int x_dtyp
                        const void* table_dev, int K, float divisor, float thr_f32, int round_to_x_dtype,
                        int idx_mode, void* stream);
 
+/* Prepared flavour (the fast path): per-channel decision tables in the x domain.
+ * Normalise -> clip -> argmin is a monotone function of x for each channel, so the LUT entry is decided by which of the
+ * K - 1 per-channel thresholds X[c][j] the element exceeds.  mctq_lut_prepare computes them exactly (bisection over f32
+ * bit patterns through the reference arithmetic: IEEE division by thr + eps, optional rounding to the activation dtype,
+ * first-minimum thresholds of the search table) together with the dequantised outputs (lut / 2^(bw - s)) * thr_c, once per
+ * quantizer; mctq_fq_lut_prepared then runs without any division or search loop.  Same reference call sites as above.
+ *   table_host        the HOST copy of the blob from mctq_lut_build_table
+ *   thr_dev           DEVICE f32 [C] (weights flavour) or NULL with scalar_mode = 1 (divisor / thr_f32 by value, C = 1)
+ *   round_dtype       0 none; 1 / 2: the normalised value is rounded to bf16 / f16 first (activation flavour)
+ *   prepared_dev      DEVICE buffer of mctq_lut_prepared_bytes(K, bw, signed, C) bytes (0 = configuration unsupported:
+ *                     more than 4096 cells, i.e. lut_values_bitwidth > 10; use the generic entry points)
+ * mctq_lut_prepare is one-off setup and synchronises `stream` once.  mctq_fq_lut_prepared needs 16-byte aligned x / y and
+ * returns MCTQ_E_RANGE when the channel window of a tile does not fit in shared memory (rows shorter than ~16
+ * elements with large K): callers fall back to mctq_fq_lut. */
+size_t mctq_lut_prepared_bytes(int K, int lut_values_bitwidth, int is_signed, int64_t C);
+int mctq_lut_prepare(const void* table_host, int K, const float* thr_dev, int64_t C, float eps, int scalar_mode,
+                     float divisor, float thr_f32, int round_dtype, void* prepared_dev, size_t prepared_bytes,
+                     void* stream);
+int mctq_fq_lut_prepared(const void* x, float* y, void* idx, int64_t n, int x_dtype, const void* prepared_dev, int K,
+                         int lut_values_bitwidth, int is_signed, int64_t C, int64_t inner, int64_t elem_offset,
+                         int idx_mode, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------
  * Host-buffer entry points: the same operators for tensors that live in HOST memory (pinned memory
  * overlaps; pageable memory works but serialises).  The data is streamed through `staging_dev`

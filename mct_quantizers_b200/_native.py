@@ -42,6 +42,9 @@ SIGNATURES = {
     "mctq_lut_build_table": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_sz]),
     "mctq_fq_lut": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_i64, c_i64, c_i64, c_f32, c_int, c_vp]),
     "mctq_fq_lut_scalar": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_f32, c_f32, c_int, c_int, c_vp]),
+    "mctq_lut_prepared_bytes": (c_sz, [c_int, c_int, c_int, c_i64]),
+    "mctq_lut_prepare": (c_int, [c_vp, c_int, c_vp, c_i64, c_f32, c_int, c_f32, c_f32, c_int, c_vp, c_sz, c_vp]),
+    "mctq_fq_lut_prepared": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_int, c_int, c_i64, c_i64, c_i64, c_int, c_vp]),
     "mctq_host_staging_min_bytes": (c_sz, []),
     "mctq_fq_affine_host": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_vp, c_sz, c_int]),
     "mctq_fq_lut_host": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_i64, c_i64, c_f32, c_int, c_f32, c_f32,

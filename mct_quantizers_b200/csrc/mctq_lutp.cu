@@ -1,0 +1,462 @@
+// mctq_lutp.cu -- "prepared" LUT fake-quant: per-channel decision tables in the x domain.
+//
+// The reference normalises every element (x / (thr + eps)), scales, clips and runs an argmin over the centroids
+// (mct_quantizers/pytorch/quantizer_utils.py:95-170).  All of that is a monotone function of x per channel, so the
+// result is decided by which of the K - 1 per-channel thresholds X[c][j] = sup{x : normalised(x) <= tau_j} the element
+// exceeds.  mctq_lut_prepare computes those thresholds EXACTLY, once per quantizer, by bisection over f32 bit patterns
+// through the reference's own arithmetic (IEEE division, optional rounding to bf16 / f16, first-minimum thresholds
+// of the search table), together with the dequantised outputs Y[c][pos] = (lut_sorted[pos] / 2^(bw-s)) * thr_c.
+// The hot kernel then needs no division and no search loop: an approximate cell index (one saturating FMA)
+// selects the single threshold that can still matter, one exact compare decides, one shared-memory load fetches y.
+#include <vector>
+
+#include "mctq_common.cuh"
+#include "mctq_lut_table.cuh"
+
+namespace mctq {
+
+constexpr uint32_t kPrepMagic = 0x4d515050u;   // 'MQPP'
+constexpr int kCellsPerUnit = 4;               // cell width = 1/4 of a step of the normalised grid
+constexpr float kCellSlop = 0.02f;             // cells; >> the 1e-4 cell error of the approximate index
+constexpr float kMagicRound = 12582912.0f;     // 1.5 * 2^23
+
+struct LutPrepHeader {      // 64 bytes, start of the prepared blob (device memory)
+    uint32_t magic;
+    int32_t K, P, NC;       // centroids, padded table size, number of cells (power of two)
+    int64_t C;
+    float mult;
+    int32_t round_dtype;    // 0 none, 1 bf16, 2 f16 (activation flavour with half-precision inputs)
+    int32_t pos0;           // sorted position of original index 0 (NaN inputs)
+    int32_t rec_floats;     // floats per channel record: X[P] Y[P] s' pad pad pad
+    int32_t off_tau, off_cq, off_cells, off_orig, off_rec;   // byte offsets into the blob
+    int32_t reserved[1];
+};
+static_assert(sizeof(LutPrepHeader) == 64, "header layout");
+
+struct PrepGeom {
+    int P, NC, rec_floats;
+    size_t off_tau, off_cq, off_cells, off_orig, off_rec, bytes;
+};
+
+static int prep_geometry(int K, int bw, int is_signed, int64_t C, PrepGeom* g) {
+    int L;
+    if (lut_geometry_from_K(K, &g->P, &L)) return MCTQ_E_LUT;
+    if (bw < 1 || bw > 16 || C < 1) return MCTQ_E_LUT;
+    const int64_t mult = 1LL << (bw - (is_signed ? 1 : 0));
+    int64_t need = kCellsPerUnit * 2 * mult + 8;
+    int64_t nc = 64;
+    while (nc < need) nc <<= 1;
+    if (nc > 4096) return MCTQ_E_RANGE;           // table would not fit comfortably in shared memory
+    g->NC = (int)nc;
+    g->rec_floats = 2 * g->P + 4;
+    size_t o = sizeof(LutPrepHeader);
+    g->off_tau = o; o += (size_t)g->P * 4;
+    g->off_cq = o; o += (size_t)g->P * 4;
+    g->off_cells = o; o += ((size_t)g->NC + 1 + 15) & ~(size_t)15;
+    g->off_orig = o; o += ((size_t)g->P + 15) & ~(size_t)15;
+    g->off_rec = o; o += (size_t)C * g->rec_floats * 4;
+    g->bytes = o;
+    return 0;
+}
+
+__host__ __device__ inline float round_like(float q, int round_dtype) {
+    if (round_dtype == 1) return __bfloat162float(__float2bfloat16_rn(q));
+    if (round_dtype == 2) return __half2float(__float2half_rn(q));
+    return q;
+}
+
+__host__ __device__ inline int32_t f2ord(float f) {
+    int32_t i = (int32_t)
+#ifdef __CUDA_ARCH__
+        __float_as_int(f);
+#else
+        [](float v) { int32_t r; memcpy(&r, &v, 4); return r; }(f);
+#endif
+    return i < 0 ? (int32_t)(0x80000000u - (uint32_t)i) : i;
+}
+__host__ __device__ inline float ord2f(int32_t o) {
+    int32_t i = o < 0 ? (int32_t)(0x80000000u - (uint32_t)o) : o;
+#ifdef __CUDA_ARCH__
+    return __int_as_float(i);
+#else
+    float f; memcpy(&f, &i, 4); return f;
+#endif
+}
+
+// ---- prepare kernel: one thread per (channel, table position)
+__global__ void __launch_bounds__(kThreads) lut_prepare_kernel(uint8_t* blob, const float* thr, float eps, int scalar_mode,
+                                                               float divisor, float thr_f32) {
+    const LutPrepHeader h = *reinterpret_cast<const LutPrepHeader*>(blob);
+    const float* tau = reinterpret_cast<const float*>(blob + h.off_tau);
+    const float* cq = reinterpret_cast<const float*>(blob + h.off_cq);
+    float* rec = reinterpret_cast<float*>(blob + h.off_rec);
+    const int64_t total = h.C * h.P;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
+        const int64_t c = i / h.P;
+        const int j = (int)(i - c * h.P);
+        float d, t;
+        if (scalar_mode) { d = divisor; t = thr_f32; }
+        else { t = thr[c]; d = __fadd_rn(t, eps); }
+        float* r = rec + c * h.rec_floats;
+        r[h.P + j] = __fmul_rn(cq[j], t);                                   // Y[c][j]
+        if (j == 0) {
+            // approximate cell scale: u = x * s' + 0.5, cell = round(u * NC)
+            r[2 * h.P] = __fdiv_rn(__fmul_rn((float)kCellsPerUnit, h.mult), d) / (float)h.NC;
+            r[2 * h.P + 1] = d;
+        }
+        float X = INFINITY;
+        if (j < h.P - 1) {
+            const float tj = tau[j];
+            if (tj == -INFINITY) X = -INFINITY;
+            else if (tj != INFINITY) {
+                // P(x) := round_like(x / d) > tau_j is monotone in x (d > 0); X = largest x for which it is false
+                auto above = [&](float x) { return round_like(__fdiv_rn(x, d), h.round_dtype) > tj; };
+                const float big = 3.4028234663852886e38f;
+                if (above(-big)) X = -INFINITY;
+                else if (!above(big)) X = big;
+                else {
+                    int64_t lo = f2ord(-big), hi = f2ord(big);
+                    while (hi - lo > 1) {
+                        int64_t mid = lo + (hi - lo) / 2;
+                        if (above(ord2f((int32_t)mid))) hi = mid; else lo = mid;
+                    }
+                    X = ord2f((int32_t)lo);
+                }
+            }
+        }
+        r[j] = X;
+    }
+}
+
+// ---- hot kernel
+struct LutPArgs {
+    const void* x;
+    float* y;
+    void* idx;
+    int64_t n;
+    const uint8_t* blob;
+    int32_t P, NC, rec_floats;
+    int32_t off_cells, off_orig, off_rec;
+    int64_t C, inner, elem_offset;
+    FastDiv div_inner, div_W;
+    uint32_t W, bigrow;
+};
+
+__device__ __forceinline__ float fma_sat(float a, float b, float c) {
+    float r;
+    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
+template <typename T, int CHMODE, int CODE, int UNROLL>
+__global__ void __launch_bounds__(kThreads) fq_lutp_kernel(const LutPArgs a) {
+    constexpr int V = 4;
+    constexpr int WORDS_IN = V * sizeof(T) / 4;
+    constexpr uint32_t TILE = kThreads * UNROLL * V;
+    extern __shared__ float sm_dyn[];                   // [records W * rec_floats][cells NC + 1 (+pad)][orig P]
+    __shared__ Window sm_win;
+    __shared__ uint32_t sm_c0;
+
+    const uint32_t tid = threadIdx.x;
+    const int64_t t0 = (int64_t)blockIdx.x * TILE;
+    const int64_t remaining = a.n - t0;
+    const bool full = remaining >= (int64_t)TILE;
+    const T* xt = reinterpret_cast<const T*>(a.x) + t0;
+
+    uint32_t w[UNROLL][WORDS_IN];
+    if (full) {
+#pragma unroll
+        for (int j = 0; j < UNROLL; ++j) ld_words<WORDS_IN>(xt + (size_t)(j * kThreads + tid) * V, w[j]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < UNROLL; ++j) {
+            int64_t l = (int64_t)(j * kThreads + tid) * V;
+            if (l + V <= remaining) ld_words<WORDS_IN>(xt + l, w[j]);
+            else {
+                T tmp[V];
+#pragma unroll
+                for (int e = 0; e < V; ++e) tmp[e] = (l + e < remaining) ? xt[l + e] : from_f32<T>(0.0f);
+                memcpy(w[j], tmp, sizeof(tmp));
+            }
+        }
+    }
+
+    const uint32_t Wn = CHMODE == CH_PT ? 1u : a.W;
+    float* sm_rec = sm_dyn;
+    uint8_t* sm_cells = reinterpret_cast<uint8_t*>(sm_dyn + (size_t)Wn * a.rec_floats);
+    uint8_t* sm_orig = sm_cells + ((a.NC + 1 + 15) & ~15);
+    {
+        // channel-independent tables: cells (NC + 1 bytes) and original indices (P bytes), copied as 32-bit words
+        const uint32_t* gc = reinterpret_cast<const uint32_t*>(a.blob + a.off_cells);
+        uint32_t* sc = reinterpret_cast<uint32_t*>(sm_cells);
+        const int words = ((a.NC + 1 + 15) & ~15) / 4;
+        for (int i = tid; i < words; i += kThreads) sc[i] = __ldg(gc + i);
+        if (CODE != 0) {
+            const uint32_t* go = reinterpret_cast<const uint32_t*>(a.blob + a.off_orig);
+            uint32_t* so = reinterpret_cast<uint32_t*>(sm_orig);
+            for (int i = tid; i < (a.P + 3) / 4; i += kThreads) so[i] = __ldg(go + i);
+        }
+    }
+    if (CHMODE == CH_PT) {
+        const float* g = reinterpret_cast<const float*>(a.blob + a.off_rec);
+        for (int k = tid; k < a.rec_floats; k += kThreads) sm_rec[k] = __ldg(g + k);
+    } else {
+        if (tid == 0) {
+            int64_t g0 = a.elem_offset + t0;
+            int64_t r0 = g0 / a.inner;
+            int64_t off = g0 - r0 * a.inner;
+            Window wv;
+            wv.off0 = a.bigrow ? 0u : (uint32_t)off;
+            int64_t sp = a.inner - off;
+            wv.split = (uint32_t)(sp > (int64_t)TILE ? (int64_t)TILE + 1 : sp);
+            sm_c0 = (uint32_t)(r0 % a.C);
+            sm_win = wv;
+        }
+        __syncthreads();
+        const uint32_t c0 = sm_c0;
+        const uint32_t total = a.W * (uint32_t)a.rec_floats;
+        const float* grec = reinterpret_cast<const float*>(a.blob + a.off_rec);
+        for (uint32_t i = tid; i < total; i += kThreads) {
+            uint32_t slot = i / (uint32_t)a.rec_floats, k = i - slot * (uint32_t)a.rec_floats;
+            uint64_t c = (uint64_t)c0 + slot;
+            c = c % (uint64_t)a.C;
+            sm_rec[i] = __ldg(grec + c * a.rec_floats + k);
+        }
+    }
+    __syncthreads();
+    Window win;
+    if (CHMODE != CH_PT) win = sm_win;
+
+    const float NCf = (float)a.NC;
+    const uint32_t rec_bytes = (uint32_t)a.rec_floats * 4u;
+    const uint32_t ybytes = (uint32_t)a.P * 4u;
+    const char* rec_base = reinterpret_cast<const char*>(sm_rec);
+    float* yt = a.y + t0;
+#pragma unroll
+    for (int j = 0; j < UNROLL; ++j) {
+        const uint32_t l = (uint32_t)(j * kThreads + tid) * V;
+        float f[V];
+        int code[V];
+        Pack<T, V>::unpack(w[j], f);
+        uint32_t slot = 0, rem = 0;
+        if (CHMODE != CH_PT) locate(l, win, a, slot, rem);
+        const char* rec = rec_base + slot * rec_bytes;
+        float sp = *reinterpret_cast<const float*>(rec + 2 * ybytes);
+        const float nan_probe = (f[0] + f[1]) + (f[2] + f[3]);     // NaN iff some element is NaN (or inf - inf)
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            if (CHMODE == CH_ELEM) {
+                if (a.bigrow) {
+                    uint32_t jrow = (l + e) >= win.split ? 1u : 0u;
+                    slot = jrow >= a.W ? jrow - a.W : jrow;
+                }
+                rec = rec_base + slot * rec_bytes;
+                sp = *reinterpret_cast<const float*>(rec + 2 * ybytes);
+            }
+            const float x = f[e];
+            const float u = fma_sat(x, sp, 0.5f);                       // saturates to [0, 1]; NaN -> 0
+            const float cf = __fmaf_rn(u, NCf, kMagicRound);            // integer cell index in the low mantissa bits
+            const uint32_t cell = __float_as_uint(cf) & 0x1fffu;
+            const uint32_t b4 = (uint32_t)sm_cells[cell] << 2;          // byte offset of the candidate threshold
+            const float X = *reinterpret_cast<const float*>(rec + b4);
+            const uint32_t p4 = b4 + ((x > X) ? 4u : 0u);
+            f[e] = *reinterpret_cast<const float*>(rec + ybytes + p4);
+            if (CODE != 0) code[e] = sm_orig[p4 >> 2];
+            if (CHMODE == CH_ELEM && !a.bigrow) {
+                if (++rem == a.div_inner.d) { rem = 0; slot = (slot + 1 == a.W) ? 0 : slot + 1; }
+            }
+        }
+        if (nan_probe != nan_probe) {
+            // rare: torch.argmin over all-NaN distances returns index 0
+            const uint32_t pos0 = (uint32_t)__ldg(&reinterpret_cast<const LutPrepHeader*>(a.blob)->pos0);
+            float g[V];
+            Pack<T, V>::unpack(w[j], g);
+            uint32_t slot2 = 0, rem2 = 0;
+            if (CHMODE != CH_PT) locate(l, win, a, slot2, rem2);
+            for (int e = 0; e < V; ++e) {
+                if (CHMODE == CH_ELEM && a.bigrow) {
+                    uint32_t jrow = (l + e) >= win.split ? 1u : 0u;
+                    slot2 = jrow >= a.W ? jrow - a.W : jrow;
+                }
+                if (g[e] != g[e]) {
+                    f[e] = *reinterpret_cast<const float*>(rec_base + slot2 * rec_bytes + ybytes + 4u * pos0);
+                    if (CODE != 0) code[e] = sm_orig[pos0];
+                }
+                if (CHMODE == CH_ELEM && !a.bigrow) {
+                    if (++rem2 == a.div_inner.d) { rem2 = 0; slot2 = (slot2 + 1 == a.W) ? 0 : slot2 + 1; }
+                }
+            }
+        }
+        if (full || (int64_t)l + V <= remaining) {
+            if (a.y) { uint32_t o[4]; Pack<float, V>::pack(f, o); st_words<4>(yt + l, o); }
+            if (CODE != 0) st_codes<V, CODE>(a.idx, t0 + l, code);
+        } else if ((int64_t)l < remaining) {
+            const int cnt = (int)(remaining - l);
+            for (int e = 0; e < V; ++e) {
+                if (e < cnt) {
+                    if (a.y) yt[l + e] = f[e];
+                    if (CODE == MCTQ_CODES_INT8) reinterpret_cast<uint8_t*>(a.idx)[t0 + l + e] = (uint8_t)code[e];
+                }
+            }
+            if (CODE == MCTQ_CODES_INT4) {
+                uint8_t* cp = reinterpret_cast<uint8_t*>(a.idx) + ((t0 + l) >> 1);
+                for (int e = 0; e < V; e += 2) {
+                    if (e < cnt) {
+                        int hi = (e + 1 < cnt) ? code[e + 1] : 0;
+                        cp[e >> 1] = (uint8_t)((code[e] & 0xf) | ((hi & 0xf) << 4));
+                    }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace mctq
+
+using namespace mctq;
+
+namespace {
+
+template <typename T, int CHMODE, int CODE>
+int launch_lutp_tiles(const LutPArgs& a_in, cudaStream_t st) {
+    constexpr int UNROLL = 4;
+    constexpr uint32_t TILE = kThreads * UNROLL * 4;
+    LutPArgs a = a_in;
+    uint32_t W = 1;
+    if (CHMODE != CH_PT) { set_window(a, TILE); W = a.W; }
+    size_t smem = (size_t)W * a.rec_floats * 4 + (((size_t)a.NC + 1 + 15) & ~(size_t)15) + (((size_t)a.P + 15) & ~(size_t)15);
+    if (smem > 64 * 1024) return MCTQ_E_RANGE;            // caller falls back to the generic kernel
+    int rc = ensure_smem(fq_lutp_kernel<T, CHMODE, CODE, UNROLL>, smem);
+    if (rc) return rc;
+    int64_t tiles = (a.n + TILE - 1) / TILE;
+    if (tiles > 0x7fffffffLL) return MCTQ_E_BADARG;
+    fq_lutp_kernel<T, CHMODE, CODE, UNROLL><<<(unsigned)tiles, kThreads, smem, st>>>(a);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cuda_rc(cudaGetLastError());
+}
+
+template <typename T>
+int launch_lutp_typed(const LutPArgs& a, int idx_mode, cudaStream_t st) {
+    int chmode;
+    if (a.C == 1) chmode = CH_PT;
+    else if (a.inner % 4 == 0 && a.elem_offset % 4 == 0) chmode = CH_VEC;
+    else chmode = CH_ELEM;
+#define MCTQ_DISPATCH_LUTP(CM)                                                             \
+    switch (idx_mode) {                                                                    \
+        case MCTQ_CODES_INT8: return launch_lutp_tiles<T, CM, MCTQ_CODES_INT8>(a, st);     \
+        case MCTQ_CODES_INT4: return launch_lutp_tiles<T, CM, MCTQ_CODES_INT4>(a, st);     \
+        default: return launch_lutp_tiles<T, CM, MCTQ_CODES_NONE>(a, st);                  \
+    }
+    if (chmode == CH_PT) { MCTQ_DISPATCH_LUTP(CH_PT) }
+    if (chmode == CH_VEC) { MCTQ_DISPATCH_LUTP(CH_VEC) }
+    MCTQ_DISPATCH_LUTP(CH_ELEM)
+#undef MCTQ_DISPATCH_LUTP
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t mctq_lut_prepared_bytes(int K, int lut_values_bitwidth, int is_signed, int64_t C) {
+    PrepGeom g;
+    if (prep_geometry(K, lut_values_bitwidth, is_signed, C, &g)) return 0;
+    return g.bytes;
+}
+
+int mctq_lut_prepare(const void* table_host, int K, const float* thr_dev, int64_t C, float eps, int scalar_mode,
+                     float divisor, float thr_f32, int round_dtype, void* prepared_dev, size_t prepared_bytes, void* stream) {
+    if (!table_host || !prepared_dev || C < 1 || (!scalar_mode && !thr_dev) || round_dtype < 0 || round_dtype > 2) return MCTQ_E_BADARG;
+    if (scalar_mode && C != 1) return MCTQ_E_BADARG;
+    const LutTableHeader* th = reinterpret_cast<const LutTableHeader*>(table_host);
+    if (th->magic != kLutMagic || th->K != K) return MCTQ_E_LUT;
+    PrepGeom g;
+    int rc = prep_geometry(K, th->bw, th->is_signed, C, &g);
+    if (rc) return rc;
+    if (prepared_bytes < g.bytes) return MCTQ_E_BADARG;
+    const int P = g.P, NC = g.NC;
+    const float* tau = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(table_host) + sizeof(LutTableHeader));
+    const float* cq = tau + (P - 1);
+    const uint8_t* orig = reinterpret_cast<const uint8_t*>(cq + P);
+    // channel-independent front of the blob, assembled on the host
+    std::vector<uint8_t> front(g.off_rec, 0);
+    LutPrepHeader* h = reinterpret_cast<LutPrepHeader*>(front.data());
+    h->magic = kPrepMagic; h->K = K; h->P = P; h->NC = NC; h->C = C; h->mult = th->mult; h->round_dtype = round_dtype;
+    h->pos0 = th->pos_of_idx0; h->rec_floats = g.rec_floats;
+    h->off_tau = (int32_t)g.off_tau; h->off_cq = (int32_t)g.off_cq; h->off_cells = (int32_t)g.off_cells;
+    h->off_orig = (int32_t)g.off_orig; h->off_rec = (int32_t)g.off_rec;
+    float* ftau = reinterpret_cast<float*>(front.data() + g.off_tau);
+    float* fcq = reinterpret_cast<float*>(front.data() + g.off_cq);
+    for (int j = 0; j < P; ++j) { ftau[j] = j < P - 1 ? tau[j] : INFINITY; fcq[j] = cq[j]; }
+    memcpy(front.data() + g.off_orig, orig, P);
+    // effective thresholds in the unrounded q domain (rounding to bf16 / f16 moves them to the rounding boundary)
+    std::vector<double> V(P - 1 > 0 ? P - 1 : 0);
+    for (int j = 0; j < P - 1; ++j) {
+        float tj = tau[j];
+        double e;
+        if (tj == INFINITY) e = INFINITY;
+        else if (tj == -INFINITY) e = -INFINITY;
+        else if (round_dtype == 0) e = tj;
+        else {
+            // largest f32 q with round_like(q) <= tau_j
+            int64_t lo = f2ord(-3.0e38f), hi = f2ord(3.0e38f);
+            if (round_like(ord2f((int32_t)lo), round_dtype) > tj) e = -INFINITY;
+            else if (!(round_like(ord2f((int32_t)hi), round_dtype) > tj)) e = INFINITY;
+            else {
+                while (hi - lo > 1) {
+                    int64_t mid = lo + (hi - lo) / 2;
+                    if (round_like(ord2f((int32_t)mid), round_dtype) > tj) hi = mid; else lo = mid;
+                }
+                e = ord2f((int32_t)lo);
+            }
+        }
+        V[j] = e * (double)kCellsPerUnit * (double)th->mult + 0.5 * NC;      // position in cell units
+    }
+    uint8_t* cells = front.data() + g.off_cells;
+    for (int k = 0; k <= NC; ++k) {
+        int b = 0;
+        for (int j = 0; j < P - 1; ++j) if (V[j] < (double)k - 0.5 - kCellSlop) ++b;
+        cells[k] = (uint8_t)b;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemcpyAsync(prepared_dev, front.data(), g.off_rec, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaStreamSynchronize(st);                 // `front` is pageable and goes out of scope; this call is one-off setup
+    if (e != cudaSuccess) return (int)e;
+    int64_t total = C * P;
+    int64_t blocks = (total + kThreads - 1) / kThreads;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    lut_prepare_kernel<<<(unsigned)blocks, kThreads, 0, st>>>(reinterpret_cast<uint8_t*>(prepared_dev), thr_dev, eps, scalar_mode, divisor, thr_f32);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cuda_rc(cudaGetLastError());
+}
+
+int mctq_fq_lut_prepared(const void* x, float* y, void* idx, int64_t n, int x_dtype, const void* prepared_dev, int K,
+                         int lut_values_bitwidth, int is_signed, int64_t C, int64_t inner, int64_t elem_offset,
+                         int idx_mode, void* stream) {
+    if (!x || !prepared_dev || n < 0 || C < 1 || inner < 1 || elem_offset < 0 || (!y && idx_mode == MCTQ_CODES_NONE)) return MCTQ_E_BADARG;
+    if (idx_mode != MCTQ_CODES_NONE && !idx) return MCTQ_E_BADARG;
+    PrepGeom g;
+    int rc = prep_geometry(K, lut_values_bitwidth, is_signed, C, &g);
+    if (rc) return rc;
+    if (idx_mode == MCTQ_CODES_INT4 && g.P > 16) return MCTQ_E_RANGE;
+    if (n == 0) return 0;
+    const size_t esz = x_dtype == MCTQ_F32 ? 4 : 2;
+    bool vec_ok = (reinterpret_cast<uintptr_t>(x) % (4 * esz)) == 0 && (!y || aligned16(y));
+    if (idx_mode != MCTQ_CODES_NONE) vec_ok = vec_ok && (reinterpret_cast<uintptr_t>(idx) & 3u) == 0;
+    if (!vec_ok) return MCTQ_E_BADARG;             // caller uses the generic entry point for misaligned views
+    LutPArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x = x; a.y = y; a.idx = idx; a.n = n; a.blob = reinterpret_cast<const uint8_t*>(prepared_dev);
+    a.P = g.P; a.NC = g.NC; a.rec_floats = g.rec_floats;
+    a.off_cells = (int32_t)g.off_cells; a.off_orig = (int32_t)g.off_orig; a.off_rec = (int32_t)g.off_rec;
+    a.C = C; a.inner = C == 1 ? 1 : inner; a.elem_offset = C == 1 ? 0 : elem_offset;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (x_dtype) {
+        case MCTQ_F32: return launch_lutp_typed<float>(a, idx_mode, st);
+        case MCTQ_BF16: return launch_lutp_typed<__nv_bfloat16>(a, idx_mode, st);
+        case MCTQ_F16: return launch_lutp_typed<__half>(a, idx_mode, st);
+        default: return MCTQ_E_DTYPE;
+    }
+}
+
+}  // extern "C"

@@ -259,8 +259,90 @@ def _dequantize_affine_cuda(codes, code_mode, is_signed, shape, scale, zero_poin
     return y
 
 
+# ---- LUT: per-device copies of the search table and per-(quantizer, device, dtype) prepared decision tables
+_LUT_DEV_TABLES = {}      # (table.data_ptr(), device) -> (table_cpu kept alive, table_dev)
+_LUT_PREPARED = {}        # key -> (objects kept alive so that data_ptr keys stay unique, prepared_dev or None)
+_ROUND_TAG = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+
+
+def clear_lut_caches():
+    _LUT_DEV_TABLES.clear()
+    _LUT_PREPARED.clear()
+
+
+def _table_header(table_cpu):
+    """(bw, is_signed) out of the search-table blob (LutTableHeader: magic, K, Ks, P, levels, pos0, bw, is_signed, ...)."""
+    hdr = table_cpu[:32].numpy().view(np.int32)
+    return int(hdr[6]), int(hdr[7])
+
+
+def _table_on(table, device):
+    if table.device == device:
+        return table
+    key = (table.data_ptr(), str(device))
+    hit = _LUT_DEV_TABLES.get(key)
+    if hit is None:
+        hit = (table, table.to(device))
+        _LUT_DEV_TABLES[key] = hit
+    return hit[1]
+
+
+def _prepared_for(table, K, device, thr_dev, eps, scalar, divisor, thr_f32, round_dtype):
+    """Device blob of per-channel decision tables for this (centroid list, thresholds, device, rounding), built once.
+    None when the configuration is outside the prepared path (lut_values_bitwidth > 10, table not on the host)."""
+    if table.device.type != 'cpu':
+        return None
+    if scalar:
+        key = (table.data_ptr(), str(device), 's', float(divisor), float(thr_f32), int(round_dtype))
+        C = 1
+    else:
+        key = (table.data_ptr(), str(device), 't', thr_dev.data_ptr(), thr_dev.numel(), float(eps))
+        C = thr_dev.numel()
+    hit = _LUT_PREPARED.get(key)
+    if hit is None:
+        lib = _native.load()
+        bw, signed = _table_header(table)
+        nbytes = lib.mctq_lut_prepared_bytes(int(K), bw, signed, C)
+        blob = None
+        if nbytes:
+            blob = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            with _on_device(device):
+                rc = lib.mctq_lut_prepare(_ptr(table), int(K), _ptr(thr_dev) if not scalar else None, C,
+                                          float(np.float32(eps)), int(scalar), float(np.float32(divisor)),
+                                          float(np.float32(thr_f32)), int(round_dtype), _ptr(blob), nbytes, _stream(device))
+            _native.check(rc, "mctq_lut_prepare")
+        hit = ((table, thr_dev), blob, bw, signed)
+        _LUT_PREPARED[key] = hit
+    return hit
+
+
+def _lut_launch(xd, y, idx, idx_mode, table, K, C, inner, thr_dev, eps, scalar, divisor, thr_f32, round_flag):
+    """Prepared kernel when possible, generic kernel otherwise."""
+    lib = _native.load()
+    tag = _dtype_tag(xd)
+    n = xd.numel()
+    round_dtype = _ROUND_TAG[xd.dtype] if (scalar and round_flag) else 0
+    prep = _prepared_for(table, K, xd.device, thr_dev, eps, scalar, divisor, thr_f32, round_dtype)
+    with _on_device(xd.device):
+        if prep is not None and prep[1] is not None:
+            rc = lib.mctq_fq_lut_prepared(_ptr(xd), _ptr(y), _ptr(idx), n, tag, _ptr(prep[1]), int(K), prep[2], prep[3],
+                                          C, inner, 0, int(idx_mode), _stream(xd.device))
+            if rc == 0:
+                return
+            if rc not in (-1, -3):                      # BADARG (misaligned view) / RANGE (window too wide): generic path
+                _native.check(rc, "mctq_fq_lut_prepared")
+        t = _table_on(table, xd.device)
+        if scalar:
+            rc = lib.mctq_fq_lut_scalar(_ptr(xd), _ptr(y), _ptr(idx), n, tag, _ptr(t), int(K), float(np.float32(divisor)),
+                                        float(np.float32(thr_f32)), int(bool(round_flag)), int(idx_mode), _stream(xd.device))
+        else:
+            rc = lib.mctq_fq_lut(_ptr(xd), _ptr(y), _ptr(idx), n, tag, _ptr(t), int(K), _ptr(thr_dev), C, inner, 0,
+                                 float(np.float32(eps)), int(idx_mode), _stream(xd.device))
+    _native.check(rc, "mctq_fq_lut")
+
+
 def _lut_tensor_launch(x, table, K, threshold, per_channel, axis, eps, idx_mode, want_values):
-    tag = _dtype_tag(x)
+    _dtype_tag(x)
     if threshold.dtype != torch.float32:
         raise RuntimeError(f"threshold must be Float, found {threshold.dtype}")
     if per_channel:
@@ -280,12 +362,8 @@ def _lut_tensor_launch(x, table, K, threshold, per_channel, axis, eps, idx_mode,
     elif idx_mode == _native.CODES_INT4:
         idx = torch.empty((n + 1) // 2, dtype=torch.uint8, device=xd.device)
     if n:
-        lib = _native.load()
-        t, thr = _param_on(table, xd.device), _param_on(threshold, xd.device)
-        with _on_device(xd.device):
-            rc = lib.mctq_fq_lut(_ptr(xd), _ptr(y), _ptr(idx), n, tag, _ptr(t), int(K), _ptr(thr), C, inner, 0,
-                                 float(np.float32(eps)), int(idx_mode), _stream(xd.device))
-        _native.check(rc, "mctq_fq_lut")
+        thr = _param_on(threshold.contiguous(), xd.device)
+        _lut_launch(xd, y, idx, idx_mode, table, K, C, inner, thr, eps, False, 1.0, 1.0, False)
     return y, idx
 
 
@@ -300,17 +378,11 @@ def _lut_indices_cuda(x, table, K, threshold, per_channel, axis, eps, idx_mode):
 
 
 def _lut_scalar_cuda(x, table, K, divisor, threshold, round_to_input_dtype):
-    tag = _dtype_tag(x)
+    _dtype_tag(x)
     xd = _dense(x)
     y = torch.empty_like(xd, dtype=torch.float32)
     if xd.numel():
-        lib = _native.load()
-        t = _param_on(table, xd.device)
-        with _on_device(xd.device):
-            rc = lib.mctq_fq_lut_scalar(_ptr(xd), _ptr(y), None, xd.numel(), tag, _ptr(t), int(K),
-                                        float(np.float32(divisor)), float(np.float32(threshold)),
-                                        int(bool(round_to_input_dtype)), 0, _stream(xd.device))
-        _native.check(rc, "mctq_fq_lut_scalar")
+        _lut_launch(xd, y, None, 0, table, K, 1, 1, None, 0.0, True, divisor, threshold, round_to_input_dtype)
     return y
 
 

@@ -36,6 +36,7 @@ class ActivationLutPOTInferableQuantizer(BaseLUTSymmetricInferableQuantizer):
     def __call__(self, inputs: torch.Tensor):
         if self._search_table is None:
             self._search_table = lut_search_table(self._lut_values_np, self.lut_values_bitwidth, self.signed)
-        table, = self._on(inputs.device, self._search_table)
+        # the table stays on the host: the operator keeps per-device copies and the prepared per-channel decision
+        # tables (nothing here touches inputs.device, so the call is fx-traceable)
         return lut_quantizer(inputs.detach(), lut_values=self.lut_values, signed=self.signed, threshold=self.threshold,
-                             lut_values_bitwidth=self.lut_values_bitwidth, eps=self.eps, _table=table)
+                             lut_values_bitwidth=self.lut_values_bitwidth, eps=self.eps, _table=self._search_table)

@@ -27,10 +27,10 @@ def lut_weights_call(q, inputs, export_fn):
         inputs.requires_grad = False
         if q._search_table is None:            # built lazily: needs the native library, which loads on first use
             q._search_table = lut_search_table(q._lut_values_np, q.lut_values_bitwidth, True)
-        thr, table = q._on(inputs.device, q._threshold_torch, q._search_table)
+        thr, = q._on(inputs.device, q._threshold_torch)
         outputs = lut_quantizer(inputs, lut_values=q._lut_values_torch, signed=True, threshold=thr,
                                 lut_values_bitwidth=q.lut_values_bitwidth, eps=q.eps, per_channel=q.per_channel,
-                                channel_axis=q.channel_axis, input_rank=q.input_rank, _table=table)
+                                channel_axis=q.channel_axis, input_rank=q.input_rank, _table=q._search_table)
     if q.enable_reuse and q.quantizer_first_run:
         q.resue_outputs = outputs
         q.quantizer_first_run = False

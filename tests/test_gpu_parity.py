@@ -91,6 +91,49 @@ def test_lut_indices_match_reference_fixture(name, lib):
         assert G.bits_equal(y.cpu().numpy().reshape(case["y"].shape), case["y"])
 
 
+@pytest.mark.parametrize("name", [n for n in CASES if n.startswith("wl_")])
+def test_prepared_lut_indices_match_reference_fixture(name):
+    """Index emission through the operator (prepared per-channel decision tables) == reference argmin assignment."""
+    from mct_quantizers_b200.pytorch.quantizer_utils import lut_search_table
+    case = G.get_case(name)
+    p = G.derive_params(case)
+    a = case["args"]
+    x = G.to_torch(case["x"], case["x_dtype"], DEV)
+    table = lut_search_table(p["lut"], p["bw"], p["signed"])
+    K = int(p["lut"].size)
+    thr = torch.from_numpy(p["thr"]).to(DEV)
+    want = case["idx"].reshape(-1)
+    n = x.numel()
+    per_channel = bool(a["per_channel"])
+    axis = a.get("channel_axis") or 0
+    idx8 = torch.ops.mctq.lut_indices(x, table, K, thr, per_channel, axis, p["eps"], 1)
+    assert np.array_equal(idx8.cpu().numpy().reshape(-1).astype(np.int32), want)
+    if K <= 16:
+        idx4 = torch.ops.mctq.lut_indices(x, table, K, thr, per_channel, axis, p["eps"], 2).cpu().numpy()
+        un = np.stack([idx4 & 0xF, idx4 >> 4], 1).reshape(-1)[:n].astype(np.int32)
+        assert np.array_equal(un, want)
+
+
+def test_prepared_lut_special_inputs(Q):
+    """NaN -> LUT index 0 (argmin over NaN distances), +-inf saturate, huge / tiny magnitudes; prepared == generic kernel."""
+    lut = [25.0, -100.0, 0.0, 127.0, -128.0, 64.0, -7.0, 3.0]           # unsorted: index 0 is not the smallest
+    thr = [0.7, 1e-3, 30.0]
+    q = Q.WeightsLUTSymmetricInferableQuantizer(3, lut, thr, True, 0, 2)
+    row = torch.tensor([float('nan'), float('inf'), -float('inf'), 3e38, -3e38, 1e-38, -1e-38, 0.0, -0.0, 0.35, float('nan'), 0.1],
+                       dtype=torch.float32)
+    x = torch.stack([row, row * 1e-3, row * 40]).to(DEV)
+    y = q(x.clone())
+    y0 = (torch.tensor(lut[0]) / 128) * torch.tensor(thr, dtype=torch.float32)
+    assert torch.equal(y[:, 0].cpu(), y0) and torch.equal(y[:, 10].cpu(), y0)
+    top = (torch.tensor(127.0) / 128) * torch.tensor(thr, dtype=torch.float32)
+    bot = (torch.tensor(-128.0) / 128) * torch.tensor(thr, dtype=torch.float32)
+    assert torch.equal(y[:, 1].cpu(), top) and torch.equal(y[:, 2].cpu(), bot)
+    finite = torch.isfinite(x)
+    want = oracle.fq_lut(np.nan_to_num(x.cpu().numpy(), nan=0.0, posinf=3e38, neginf=-3e38), oracle.F32, np.asarray(lut, np.float32),
+                         np.asarray(thr, np.float32), 3, 12, 8, True, 1e-8)
+    assert np.array_equal(y.cpu().numpy()[finite.cpu().numpy()], want[finite.cpu().numpy()])
+
+
 # ------------------------------------------------------------------------------------------- raw C ABI vs oracle
 def _rand_x(rng, n, dtype, scale=1.0):
     v = (rng.standard_normal(n) * scale).astype(np.float32)

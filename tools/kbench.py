@@ -123,6 +123,21 @@ def main():
                                    args.reps, nbuf)
                 report(f"lut K=16 activation scalar u{u}", dt, n * (es + 4), med, best)
             lib.mctq_set_tuning(0, 4)
+            # prepared path: per-channel decision tables in the x domain (built once, outside the timed region)
+            table_host = lut_search_table(lut, 8, True)
+            for (C, inner, label) in ((4096, 11008, "rows 11008"), (11008, 4096, "rows 4096"), (1, 1, "per-tensor"), (65536, 64, "rows 64")):
+                thr = torch.rand(C, device=dev) * 0.05 + 0.06
+                nb = lib.mctq_lut_prepared_bytes(16, 8, 1, C)
+                blob = torch.empty(nb, dtype=torch.uint8, device=dev)
+                rc = lib.mctq_lut_prepare(vp(table_host), 16, vp(thr), C, 1e-8, 0, 1.0, 1.0, 0, vp(blob), nb, stream())
+                assert rc == 0, rc
+                torch.cuda.synchronize()
+                for mode, lab in ((0, ""), (2, " + int4 idx")):
+                    ib = torch.empty(n // 2 + 8, dtype=torch.uint8, device=dev) if mode else None
+                    fn = lambda i: lib.mctq_fq_lut_prepared(vp(xs[i]), vp(yf[i]), vp(ib), n, tag, vp(blob), 16, 8, 1, C, inner, 0, mode, stream())
+                    assert fn(0) == 0
+                    med, best = timeit(fn, args.reps, nbuf)
+                    report(f"lut-prepared K=16 weights {label}{lab}", dt, n * (es + 4 + (0.5 if mode else 0)), med, best)
             lib.mctq_set_tuning(2, 1)
             thr = torch.rand(4096, device=dev) * 0.05 + 0.06
             med, best = timeit(lambda i: lib.mctq_fq_lut(vp(xs[i]), vp(yf[i]), None, n, tag, vp(table), 16, vp(thr), 4096, 11008, 0, 1e-8, 0, stream()),
