@@ -95,6 +95,8 @@ __global__ void __launch_bounds__(kThreads) fq_affine_kernel(const AffineArgs a)
     const int64_t remaining = a.n - t0;
     const bool full = remaining >= (int64_t)TILE;
     const T* xt = reinterpret_cast<const T*>(a.x) + t0;
+    pdl_wait();
+    pdl_launch_dependents();
 
     uint32_t w[UNROLL][WORDS];
     if (full) {
@@ -256,6 +258,8 @@ __device__ __forceinline__ void multi_tile_body(const MctqTensorDesc& d, int64_t
 
 __global__ void __launch_bounds__(kThreads) fq_affine_multi_kernel(const MctqTensorDesc* __restrict__ descs,
                                                                    const int32_t* __restrict__ tile_starts, int n_desc) {
+    pdl_wait();
+    pdl_launch_dependents();
     // which tensor does this tile belong to?  upper-bound binary search over tile_starts
     const int tile = blockIdx.x;
     int lo = 0, hi = n_desc;
@@ -304,9 +308,7 @@ int launch_affine_tiles(const AffineArgs& a_in, cudaStream_t st) {
     }
     int64_t tiles = (a.n + TILE - 1) / TILE;
     if (tiles > 0x7fffffffLL) return MCTQ_E_BADARG;
-    fq_affine_kernel<T, CHMODE, CODE, UNROLL, RINT><<<(unsigned)tiles, kThreads, smem, st>>>(a);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    return cuda_rc(cudaGetLastError());
+    return launch_streaming(fq_affine_kernel<T, CHMODE, CODE, UNROLL, RINT>, (unsigned)tiles, smem, st, a);
 }
 
 template <typename T, int CHMODE, int CODE, bool RINT>
@@ -430,9 +432,7 @@ int mctq_fq_affine_multi(const MctqTensorDesc* descs_dev, const int32_t* tile_st
                          int64_t total_tiles, void* stream) {
     if (!descs_dev || !tile_starts_dev || n_desc < 1 || total_tiles < 0 || total_tiles > 0x7fffffffLL) return MCTQ_E_BADARG;
     if (total_tiles == 0) return 0;
-    fq_affine_multi_kernel<<<(unsigned)total_tiles, kThreads, 0, (cudaStream_t)stream>>>(descs_dev, tile_starts_dev, n_desc);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    return cuda_rc(cudaGetLastError());
+    return launch_streaming(fq_affine_multi_kernel, (unsigned)total_tiles, 0, (cudaStream_t)stream, descs_dev, tile_starts_dev, n_desc);
 }
 
 }  // extern "C"

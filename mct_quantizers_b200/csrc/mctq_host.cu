@@ -6,6 +6,7 @@ std::atomic<int64_t> g_launches{0};
 int g_unroll = 4;
 int g_force_rint = 0;
 int g_force_ieee_div = 0;
+int g_pdl = 1;
 }  // namespace mctq
 
 using namespace mctq;
@@ -26,6 +27,7 @@ int mctq_set_tuning(int key, int value) {
         case 0: prev = g_unroll; if (value != 2 && value != 4 && value != 8) return MCTQ_E_BADARG; g_unroll = value; return prev;
         case 1: prev = g_force_rint; g_force_rint = value ? 1 : 0; return prev;
         case 2: prev = g_force_ieee_div; g_force_ieee_div = value ? 1 : 0; return prev;
+        case 3: prev = g_pdl; g_pdl = value ? 1 : 0; return prev;
         default: return MCTQ_E_BADARG;
     }
 }
@@ -33,7 +35,7 @@ int mctq_set_tuning(int key, int value) {
 // ---------------------------------------------------------------------------------------------- host staging
 namespace {
 constexpr int kHostStreams = 3;
-constexpr size_t kHostChunkBytesIn = 32u << 20;      // input bytes per chunk
+constexpr size_t kHostChunkBytesIn = 32u << 20;      // largest input chunk (slot size); small tensors use smaller chunks
 struct HostCtx {
     int device = -1;
     cudaStream_t st[kHostStreams] = {nullptr, nullptr, nullptr};
@@ -56,6 +58,17 @@ int host_ctx(int device, HostCtx** out) {
     return 0;
 }
 size_t dtype_size(int dt) { return dt == MCTQ_F32 ? 4 : 2; }
+
+// chunk length: about an eighth of the tensor so that uploads, kernels and downloads of neighbouring chunks overlap
+// even for tensors of a few tens of MB, between 1 MB and the slot size, a multiple of 64 Ki elements
+int64_t pick_chunk_elems(int64_t n, size_t in_elem_bytes, size_t slot_elem_bytes) {
+    const int64_t max_elems = (int64_t)(kHostChunkBytesIn / slot_elem_bytes);
+    const int64_t min_elems = (int64_t)((1u << 20) / in_elem_bytes);
+    int64_t c = (n / 8 + 65535) / 65536 * 65536;
+    if (c < min_elems) c = min_elems;
+    if (c > max_elems) c = max_elems;
+    return c;
+}
 }  // namespace
 
 size_t mctq_host_staging_min_bytes(void) {
@@ -88,7 +101,7 @@ int mctq_fq_affine_host(const void* x_host, void* y_host, int64_t n, int x_dtype
     if (e != cudaSuccess) return (int)e;
     cudaEventRecord(ev, ctx->st[0]);
     for (int i = 1; i < kHostStreams; ++i) cudaStreamWaitEvent(ctx->st[i], ev, 0);
-    const int64_t chunk_elems = (int64_t)(kHostChunkBytesIn / es);
+    const int64_t chunk_elems = pick_chunk_elems(n, es, es);
     int k = 0;
     for (int64_t off = 0; off < n; off += chunk_elems, ++k) {
         const int64_t cnt = (n - off) < chunk_elems ? (n - off) : chunk_elems;
@@ -138,7 +151,7 @@ int mctq_fq_lut_host(const void* x_host, float* y_host, int64_t n, int x_dtype, 
     if (e != cudaSuccess) return (int)e;
     cudaEventRecord(ev, ctx->st[0]);
     for (int i = 1; i < kHostStreams; ++i) cudaStreamWaitEvent(ctx->st[i], ev, 0);
-    const int64_t chunk_elems = (int64_t)(kHostChunkBytesIn / 4);   // output chunk is f32: bound by it
+    const int64_t chunk_elems = pick_chunk_elems(n, es, 4);   // output chunk is f32: the slot is bound by it
     int k = 0;
     for (int64_t off = 0; off < n; off += chunk_elems, ++k) {
         const int64_t cnt = (n - off) < chunk_elems ? (n - off) : chunk_elems;

@@ -147,6 +147,23 @@ def main():
             del yf
         del xs
         torch.cuda.empty_cache()
+    if "gaps" in what:
+        # launch-gap experiment: 64 back-to-back launches of a small (64 MB) and a medium (256 MB) tensor, PDL on / off
+        for mb in (16, 64, 256):
+            n = int(mb * 1e6 / 4) // 4096 * 4096
+            xs = [torch.empty(n, device=dev).uniform_(-50, 50) for _ in range(8)]
+            ys = [torch.empty(n, device=dev) for _ in range(8)]
+            for pdl in (0, 1):
+                lib.mctq_set_tuning(3, pdl)
+                def burst(_):
+                    for k in range(64):
+                        lib.mctq_fq_affine_scalar(vp(xs[k % 8]), vp(ys[k % 8]), None, n, 0, 0.0129, 77, 0, 255, 0, stream())
+                med, best = timeit(burst, 10, 1)
+                gbs = 64 * 8 * n / med / 1e6
+                print(f"64 back-to-back launches of {mb} MB f32, PDL={pdl}: {med / 64 * 1e3:8.2f} us per launch  {gbs:8.1f} GB/s", flush=True)
+                rows.append({"kernel": f"burst64 {mb}MB pdl={pdl}", "us_per_launch": round(med / 64 * 1e3, 2), "GBs": round(gbs, 1)})
+            lib.mctq_set_tuning(3, 1)
+            del xs, ys
     if args.json:
         with open(args.json, "w") as f:
             json.dump({"peak_gbs": peak, "rows": rows}, f, indent=1)
