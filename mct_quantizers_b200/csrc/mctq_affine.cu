@@ -21,6 +21,10 @@ struct AffineArgs {
     FastDiv div_inner, div_W;
     uint32_t W;             // staged channel slots
     uint32_t bigrow;        // inner >= tile elems: a tile touches at most two rows
+    // CH_LAST (channel is the innermost dimension): parameters are staged for one period = lcm(C, V) of the channel
+    // pattern, so that every aligned vector of V elements reads V consecutive entries
+    uint32_t period;
+    FastDiv div_period;
 };
 
 template <bool RINT> struct AffineOp {
@@ -87,7 +91,7 @@ __global__ void __launch_bounds__(kThreads) fq_affine_kernel(const AffineArgs a)
     constexpr int V = 16 / sizeof(T);
     constexpr int WORDS = 4;
     constexpr uint32_t TILE = kThreads * UNROLL * V;
-    extern __shared__ float sm_par[];
+    extern __shared__ __align__(16) float sm_par[];
     __shared__ Window sm_win;
 
     const uint32_t tid = threadIdx.x;
@@ -118,8 +122,21 @@ __global__ void __launch_bounds__(kThreads) fq_affine_kernel(const AffineArgs a)
 
     typename Op::ChanParams pu;
     Window win;
+    uint32_t base_mod = 0;
+    bool has_zp = true;
     if (CHMODE == CH_PT) {
         pu = Op::uniform(a);
+    } else if (CHMODE == CH_LAST) {
+        // entry i of the period holds the parameters of channel i % C (struct of arrays: inv | s | zp)
+        int any_zp = 0;
+        for (uint32_t i = tid; i < a.period; i += kThreads) {
+            const uint32_t c = i - fdiv_u32(i, a.div_W) * a.div_W.d;              // div_W divides by C here
+            Op::stage(sm_par, a.period, i, (int64_t)c, a);
+            any_zp |= __ldg(a.zp + c);
+        }
+        base_mod = (uint32_t)((uint64_t)(a.elem_offset + t0) % a.period);
+        // symmetric quantizers have all-zero zero points: then a third of the shared-memory reads can be skipped
+        has_zp = __syncthreads_or(any_zp) != 0;
     } else {
         stage_window<Op>(sm_par, &sm_win, a.elem_offset + t0, TILE, a);
         __syncthreads();
@@ -136,6 +153,27 @@ __global__ void __launch_bounds__(kThreads) fq_affine_kernel(const AffineArgs a)
         if (CHMODE == CH_PT) {
 #pragma unroll
             for (int e = 0; e < V; ++e) f[e] = Op::template apply<CODE != 0>(f[e], pu, code[e]);
+        } else if (CHMODE == CH_LAST) {
+            const uint32_t m = base_mod + l;
+            const uint32_t i0 = m - fdiv_u32(m, a.div_period) * a.period;            // multiple of V: vector loads below
+            float pinv[V], ps[V], pz[V];
+#pragma unroll
+            for (int e = 0; e < V; e += 4) {
+                *reinterpret_cast<float4*>(&pinv[e]) = *reinterpret_cast<const float4*>(&sm_par[i0 + e]);
+                *reinterpret_cast<float4*>(&ps[e]) = *reinterpret_cast<const float4*>(&sm_par[a.period + i0 + e]);
+                if (has_zp) *reinterpret_cast<float4*>(&pz[e]) = *reinterpret_cast<const float4*>(&sm_par[2 * a.period + i0 + e]);
+                else *reinterpret_cast<float4*>(&pz[e]) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                typename Op::ChanParams p;
+                p.inv = pinv[e];
+                p.s = ps[e];
+                p.zp = __float_as_int(pz[e]);
+                if (RINT) { p.lo = (float)a.qmin; p.hi = (float)a.qmax; }
+                else { p.lo = (float)(a.qmin - p.zp); p.hi = (float)(a.qmax - p.zp); }
+                f[e] = Op::template apply<CODE != 0>(f[e], p, code[e]);
+            }
         } else if (CHMODE == CH_VEC) {
             uint32_t slot, rem;
             locate(l, win, a, slot, rem);
@@ -300,7 +338,13 @@ int launch_affine_tiles(const AffineArgs& a_in, cudaStream_t st) {
     constexpr uint32_t TILE = kThreads * UNROLL * V;
     AffineArgs a = a_in;
     size_t smem = 0;
-    if (CHMODE != CH_PT) {
+    if (CHMODE == CH_LAST) {
+        a.div_W = make_fastdiv((uint32_t)a.C);
+        a.div_period = make_fastdiv(a.period);
+        smem = (size_t)a.period * 3 * sizeof(float);
+        int rc = ensure_smem(fq_affine_kernel<T, CHMODE, CODE, UNROLL, RINT>, smem);
+        if (rc) return rc;
+    } else if (CHMODE != CH_PT) {
         set_window(a, TILE);
         smem = (size_t)a.W * 3 * sizeof(float);
         int rc = ensure_smem(fq_affine_kernel<T, CHMODE, CODE, UNROLL, RINT>, smem);
@@ -347,13 +391,24 @@ int launch_affine_typed(const AffineArgs& a, int code_mode, cudaStream_t st) {
         return cuda_rc(cudaGetLastError());
     }
     int chmode;
+    AffineArgs a2 = a;
     if (a.C == 1) chmode = CH_PT;
     else if (a.inner % V == 0 && a.elem_offset % V == 0) chmode = CH_VEC;
-    else chmode = CH_ELEM;
+    else {
+        chmode = CH_ELEM;
+        if (a.inner == 1 && a.elem_offset % V == 0 && a.C <= 4096) {
+            // channel-innermost layout: one period of the channel pattern (lcm(C, V) entries, <= 48 KB) in shared memory
+            uint64_t g = (uint64_t)a.C, h = V;
+            while (h) { uint64_t t = g % h; g = h; h = t; }
+            const uint64_t period = (uint64_t)a.C / g * V;
+            if (period <= 4096) { chmode = CH_LAST; a2.period = (uint32_t)period; }
+        }
+    }
 #define MCTQ_DISPATCH_AFF(CM)                                                                   \
-    return rint_path ? launch_affine_code<T, CM, true>(a, code_mode, st) : launch_affine_code<T, CM, false>(a, code_mode, st)
+    return rint_path ? launch_affine_code<T, CM, true>(a2, code_mode, st) : launch_affine_code<T, CM, false>(a2, code_mode, st)
     if (chmode == CH_PT) { MCTQ_DISPATCH_AFF(CH_PT); }
     if (chmode == CH_VEC) { MCTQ_DISPATCH_AFF(CH_VEC); }
+    if (chmode == CH_LAST) { MCTQ_DISPATCH_AFF(CH_LAST); }
     MCTQ_DISPATCH_AFF(CH_ELEM);
 #undef MCTQ_DISPATCH_AFF
 }

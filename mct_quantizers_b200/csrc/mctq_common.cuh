@@ -31,7 +31,7 @@ extern int g_force_rint;
 extern int g_force_ieee_div;
 extern int g_pdl;           // programmatic dependent launch for the streaming kernels (mctq_set_tuning key 3)
 
-enum ChMode { CH_PT = 0, CH_VEC = 1, CH_ELEM = 2 };
+enum ChMode { CH_PT = 0, CH_VEC = 1, CH_ELEM = 2, CH_LAST = 3 };
 
 // ------------------------------------------------------------------------------------------ small utils
 struct FastDiv {   // floor(u / d) for 0 <= u < 2^31, 1 <= d < 2^31  (round-up multiplier, Granlund-Montgomery)

@@ -32,6 +32,8 @@ int mctq_set_tuning(int key, int value) {
     }
 }
 
+}  // extern "C"
+
 // ---------------------------------------------------------------------------------------------- host staging
 namespace {
 constexpr int kHostStreams = 3;
@@ -39,6 +41,7 @@ constexpr size_t kHostChunkBytesIn = 32u << 20;      // largest input chunk (slo
 struct HostCtx {
     int device = -1;
     cudaStream_t st[kHostStreams] = {nullptr, nullptr, nullptr};
+    cudaEvent_t params_ready = nullptr;
 };
 HostCtx g_hctx[16];
 
@@ -52,6 +55,8 @@ int host_ctx(int device, HostCtx** out) {
             e = cudaStreamCreateWithFlags(&c.st[i], cudaStreamNonBlocking);
             if (e != cudaSuccess) return (int)e;
         }
+        e = cudaEventCreateWithFlags(&c.params_ready, cudaEventDisableTiming);
+        if (e != cudaSuccess) return (int)e;
         c.device = device;
     }
     *out = &c;
@@ -60,7 +65,7 @@ int host_ctx(int device, HostCtx** out) {
 size_t dtype_size(int dt) { return dt == MCTQ_F32 ? 4 : 2; }
 
 // chunk length: about an eighth of the tensor so that uploads, kernels and downloads of neighbouring chunks overlap
-// even for tensors of a few tens of MB, between 1 MB and the slot size, a multiple of 64 Ki elements
+// even for tensors of a few tens of MB, between 1 MB of input and the slot size, a multiple of 64 Ki elements
 int64_t pick_chunk_elems(int64_t n, size_t in_elem_bytes, size_t slot_elem_bytes) {
     const int64_t max_elems = (int64_t)(kHostChunkBytesIn / slot_elem_bytes);
     const int64_t min_elems = (int64_t)((1u << 20) / in_elem_bytes);
@@ -69,7 +74,46 @@ int64_t pick_chunk_elems(int64_t n, size_t in_elem_bytes, size_t slot_elem_bytes
     if (c > max_elems) c = max_elems;
     return c;
 }
+
+// H2D -> launch(chunk) -> D2H for every chunk, round-robin over the internal streams; returns when y_host is complete.
+// `launch(d_in, d_out, count, elem_offset, stream)` enqueues the kernel for one chunk.  `params_on_stream0`: the caller
+// has enqueued parameter uploads on stream 0 that the other streams must wait for.
+template <class Launch>
+int run_pipeline(HostCtx* ctx, uint8_t* slots, const uint8_t* x_host, uint8_t* y_host, int64_t n, size_t in_es, size_t out_es,
+                 bool params_on_stream0, Launch launch) {
+    cudaError_t e = cudaSuccess;
+    int rc = 0;
+    const int64_t chunk_elems = pick_chunk_elems(n, in_es, in_es > out_es ? in_es : out_es);
+    const int64_t n_chunks = (n + chunk_elems - 1) / chunk_elems;
+    const int used = (int)(n_chunks < kHostStreams ? n_chunks : kHostStreams);
+    if (params_on_stream0 && used > 1) {
+        cudaEventRecord(ctx->params_ready, ctx->st[0]);
+        for (int i = 1; i < used; ++i) cudaStreamWaitEvent(ctx->st[i], ctx->params_ready, 0);
+    }
+    int k = 0;
+    for (int64_t off = 0; off < n; off += chunk_elems, ++k) {
+        const int64_t cnt = (n - off) < chunk_elems ? (n - off) : chunk_elems;
+        cudaStream_t st = ctx->st[k % kHostStreams];
+        uint8_t* d_in = slots + (size_t)(k % kHostStreams) * 3 * kHostChunkBytesIn;
+        uint8_t* d_out = d_in + kHostChunkBytesIn;
+        e = cudaMemcpyAsync(d_in, x_host + off * in_es, cnt * in_es, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) break;
+        rc = launch(d_in, d_out, cnt, off, st);
+        if (rc) break;
+        e = cudaMemcpyAsync(y_host + off * out_es, d_out, cnt * out_es, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) break;
+    }
+    for (int i = 0; i < kHostStreams; ++i) {
+        if (i >= used && !(i == 0 && params_on_stream0)) continue;
+        cudaError_t e2 = cudaStreamSynchronize(ctx->st[i]);
+        if (e == cudaSuccess && e2 != cudaSuccess) e = e2;
+    }
+    if (rc) return rc;
+    return cuda_rc(e);
+}
 }  // namespace
+
+extern "C" {
 
 size_t mctq_host_staging_min_bytes(void) {
     // per stream: one input chunk + one f32-sized output chunk (LUT output of a 2-byte input is 2x larger) + parameter area
@@ -82,46 +126,33 @@ int mctq_fq_affine_host(const void* x_host, void* y_host, int64_t n, int x_dtype
     if (!x_host || !y_host || !scale_host || !zp_host || !staging_dev || n < 0 || C < 1 || inner < 1) return MCTQ_E_BADARG;
     if (x_dtype < 0 || x_dtype > 2) return MCTQ_E_DTYPE;
     if (staging_bytes < mctq_host_staging_min_bytes() || (size_t)C * 8 > (4u << 20)) return MCTQ_E_BADARG;
+    if (n == 0) return 0;
     HostCtx* ctx;
     int rc = host_ctx(device, &ctx);
     if (rc) return rc;
     const size_t es = dtype_size(x_dtype);
     uint8_t* base = reinterpret_cast<uint8_t*>(staging_dev);
+    uint8_t* slots = base + (4u << 20);
+    if (C == 1) {
+        // per-tensor: parameters travel by value, nothing to upload
+        const float s = scale_host[0];
+        const int32_t z = zp_host[0];
+        return run_pipeline(ctx, slots, reinterpret_cast<const uint8_t*>(x_host), reinterpret_cast<uint8_t*>(y_host), n, es, es, false,
+                            [&](uint8_t* d_in, uint8_t* d_out, int64_t cnt, int64_t, cudaStream_t st) {
+                                return mctq_fq_affine_scalar(d_in, d_out, nullptr, cnt, x_dtype, s, z, qmin, qmax, MCTQ_CODES_NONE, st);
+                            });
+    }
     float* d_scale = reinterpret_cast<float*>(base);
     int32_t* d_zp = reinterpret_cast<int32_t*>(base + (2u << 20));
-    uint8_t* slots = base + (4u << 20);
-    cudaError_t e;
-    // parameters go first on stream 0; the other streams wait for them through an event
-    e = cudaMemcpyAsync(d_scale, scale_host, (size_t)C * 4, cudaMemcpyHostToDevice, ctx->st[0]);
+    cudaError_t e = cudaMemcpyAsync(d_scale, scale_host, (size_t)C * 4, cudaMemcpyHostToDevice, ctx->st[0]);
     if (e != cudaSuccess) return (int)e;
     e = cudaMemcpyAsync(d_zp, zp_host, (size_t)C * 4, cudaMemcpyHostToDevice, ctx->st[0]);
     if (e != cudaSuccess) return (int)e;
-    cudaEvent_t ev;
-    e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-    if (e != cudaSuccess) return (int)e;
-    cudaEventRecord(ev, ctx->st[0]);
-    for (int i = 1; i < kHostStreams; ++i) cudaStreamWaitEvent(ctx->st[i], ev, 0);
-    const int64_t chunk_elems = pick_chunk_elems(n, es, es);
-    int k = 0;
-    for (int64_t off = 0; off < n; off += chunk_elems, ++k) {
-        const int64_t cnt = (n - off) < chunk_elems ? (n - off) : chunk_elems;
-        cudaStream_t st = ctx->st[k % kHostStreams];
-        uint8_t* d_in = slots + (size_t)(k % kHostStreams) * 3 * kHostChunkBytesIn;
-        uint8_t* d_out = d_in + kHostChunkBytesIn;
-        e = cudaMemcpyAsync(d_in, reinterpret_cast<const uint8_t*>(x_host) + off * es, cnt * es, cudaMemcpyHostToDevice, st);
-        if (e != cudaSuccess) break;
-        rc = mctq_fq_affine(d_in, d_out, nullptr, cnt, x_dtype, d_scale, d_zp, C, inner, off, qmin, qmax, MCTQ_CODES_NONE, st);
-        if (rc) break;
-        e = cudaMemcpyAsync(reinterpret_cast<uint8_t*>(y_host) + off * es, d_out, cnt * es, cudaMemcpyDeviceToHost, st);
-        if (e != cudaSuccess) break;
-    }
-    for (int i = 0; i < kHostStreams; ++i) {
-        cudaError_t e2 = cudaStreamSynchronize(ctx->st[i]);
-        if (e == cudaSuccess && e2 != cudaSuccess) e = e2;
-    }
-    cudaEventDestroy(ev);
-    if (rc) return rc;
-    return cuda_rc(e);
+    return run_pipeline(ctx, slots, reinterpret_cast<const uint8_t*>(x_host), reinterpret_cast<uint8_t*>(y_host), n, es, es, true,
+                        [&](uint8_t* d_in, uint8_t* d_out, int64_t cnt, int64_t off, cudaStream_t st) {
+                            return mctq_fq_affine(d_in, d_out, nullptr, cnt, x_dtype, d_scale, d_zp, C, inner, off, qmin, qmax,
+                                                  MCTQ_CODES_NONE, st);
+                        });
 }
 
 int mctq_fq_lut_host(const void* x_host, float* y_host, int64_t n, int x_dtype, const void* table_host, int K,
@@ -133,6 +164,7 @@ int mctq_fq_lut_host(const void* x_host, float* y_host, int64_t n, int x_dtype, 
     const size_t tbytes = mctq_lut_table_bytes(K);
     if (!tbytes || tbytes > (1u << 20)) return MCTQ_E_LUT;
     if (staging_bytes < mctq_host_staging_min_bytes() || (size_t)C * 4 > (2u << 20)) return MCTQ_E_BADARG;
+    if (n == 0) return 0;
     HostCtx* ctx;
     int rc = host_ctx(device, &ctx);
     if (rc) return rc;
@@ -146,33 +178,14 @@ int mctq_fq_lut_host(const void* x_host, float* y_host, int64_t n, int x_dtype, 
     if (e != cudaSuccess) return (int)e;
     e = cudaMemcpyAsync(d_table, table_host, tbytes, cudaMemcpyHostToDevice, ctx->st[0]);
     if (e != cudaSuccess) return (int)e;
-    cudaEvent_t ev;
-    e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-    if (e != cudaSuccess) return (int)e;
-    cudaEventRecord(ev, ctx->st[0]);
-    for (int i = 1; i < kHostStreams; ++i) cudaStreamWaitEvent(ctx->st[i], ev, 0);
-    const int64_t chunk_elems = pick_chunk_elems(n, es, 4);   // output chunk is f32: the slot is bound by it
-    int k = 0;
-    for (int64_t off = 0; off < n; off += chunk_elems, ++k) {
-        const int64_t cnt = (n - off) < chunk_elems ? (n - off) : chunk_elems;
-        cudaStream_t st = ctx->st[k % kHostStreams];
-        uint8_t* d_in = slots + (size_t)(k % kHostStreams) * 3 * kHostChunkBytesIn;
-        float* d_out = reinterpret_cast<float*>(d_in + kHostChunkBytesIn);
-        e = cudaMemcpyAsync(d_in, reinterpret_cast<const uint8_t*>(x_host) + off * es, cnt * es, cudaMemcpyHostToDevice, st);
-        if (e != cudaSuccess) break;
-        if (scalar_mode) rc = mctq_fq_lut_scalar(d_in, d_out, nullptr, cnt, x_dtype, d_table, K, divisor, thr_f32, round_to_x_dtype, MCTQ_CODES_NONE, st);
-        else rc = mctq_fq_lut(d_in, d_out, nullptr, cnt, x_dtype, d_table, K, d_thr, C, inner, off, eps, MCTQ_CODES_NONE, st);
-        if (rc) break;
-        e = cudaMemcpyAsync(y_host + off, d_out, cnt * 4, cudaMemcpyDeviceToHost, st);
-        if (e != cudaSuccess) break;
-    }
-    for (int i = 0; i < kHostStreams; ++i) {
-        cudaError_t e2 = cudaStreamSynchronize(ctx->st[i]);
-        if (e == cudaSuccess && e2 != cudaSuccess) e = e2;
-    }
-    cudaEventDestroy(ev);
-    if (rc) return rc;
-    return cuda_rc(e);
+    return run_pipeline(ctx, slots, reinterpret_cast<const uint8_t*>(x_host), reinterpret_cast<uint8_t*>(y_host), n, es, 4, true,
+                        [&](uint8_t* d_in, uint8_t* d_out, int64_t cnt, int64_t off, cudaStream_t st) {
+                            float* out = reinterpret_cast<float*>(d_out);
+                            if (scalar_mode)
+                                return mctq_fq_lut_scalar(d_in, out, nullptr, cnt, x_dtype, d_table, K, divisor, thr_f32, round_to_x_dtype,
+                                                          MCTQ_CODES_NONE, st);
+                            return mctq_fq_lut(d_in, out, nullptr, cnt, x_dtype, d_table, K, d_thr, C, inner, off, eps, MCTQ_CODES_NONE, st);
+                        });
 }
 
 }  // extern "C"

@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(kThreads) fq_lutp_kernel(const LutPArgs a) {
     constexpr int V = 4;
     constexpr int WORDS_IN = V * sizeof(T) / 4;
     constexpr uint32_t TILE = kThreads * UNROLL * V;
-    extern __shared__ float sm_dyn[];                   // [records W * rec_floats][cells NC + 1 (+pad)][orig P]
+    extern __shared__ __align__(16) float sm_dyn[];                   // [records W * rec_floats][cells NC + 1 (+pad)][orig P]
     __shared__ Window sm_win;
     __shared__ uint32_t sm_c0;
 

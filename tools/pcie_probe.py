@@ -1,0 +1,50 @@
+#!/usr/bin/env python
+"""Host-link ceiling for the e2e number: pinned H2D, D2H and both at once (GB/s), plus the host-staging operator
+on one large and one small tensor."""
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mct_quantizers_b200.pytorch import quantizers as Q  # noqa: E402
+
+dev = torch.device("cuda:0")
+n = 256 << 20   # 1 GiB of f32
+h_in = torch.empty(n, dtype=torch.float32, pin_memory=True).normal_()
+h_out = torch.empty(n, dtype=torch.float32, pin_memory=True)
+d_a = torch.empty(n, dtype=torch.float32, device=dev)
+d_b = torch.empty(n, dtype=torch.float32, device=dev)
+s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+
+def t(fn, reps=5):
+    fn()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / reps
+
+
+gb = n * 4 / 1e9
+print(f"H2D alone   : {gb / t(lambda: d_a.copy_(h_in, non_blocking=True)):6.1f} GB/s")
+print(f"D2H alone   : {gb / t(lambda: h_out.copy_(d_b, non_blocking=True)):6.1f} GB/s")
+
+
+def both():
+    with torch.cuda.stream(s1):
+        d_a.copy_(h_in, non_blocking=True)
+    with torch.cuda.stream(s2):
+        h_out.copy_(d_b, non_blocking=True)
+
+
+dt = t(both)
+print(f"H2D + D2H   : {gb / dt:6.1f} GB/s per direction, {2 * gb / dt:6.1f} GB/s total  (the e2e ceiling in algorithmic GB/s)")
+q = Q.ActivationUniformInferableQuantizer(8, [-2.5], [3.0])
+for elems in (n, 64 << 20, 16 << 20, 4 << 20, 1 << 20):
+    x = h_in[:elems]
+    dt = t(lambda: q(x), reps=5)
+    print(f"host-staged fake-quant of {elems * 4 / 1e6:8.1f} MB: {dt * 1e3:8.3f} ms  {2 * elems * 4 / dt / 1e9:6.1f} GB/s algorithmic")
