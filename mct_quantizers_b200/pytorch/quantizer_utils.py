@@ -91,8 +91,10 @@ def lut_quantizer(tensor_data: torch.Tensor,
     normalise by (threshold + eps) into the 2^lut_values_bitwidth grid, clip, pick the first nearest LUT
     entry, scale back by threshold.  `threshold` is an f32 tensor (weights) or a Python float (activations).
     One fused kernel; f32 output."""
+    from mct_quantizers_b200 import ops
     K = int(lut_values.numel())
     table = _table if _table is not None else lut_search_table(lut_values.detach().cpu().numpy(), lut_values_bitwidth, signed)
+    direct = ops.direct_ok(tensor_data)       # plain CUDA tensor and nobody tracing: skip the dispatcher (~10 us)
     if isinstance(threshold, torch.Tensor):
         thr = threshold.reshape(-1)
         if thr.dtype != torch.float32:
@@ -100,10 +102,12 @@ def lut_quantizer(tensor_data: torch.Tensor,
         if per_channel:
             if input_rank is not None and input_rank != tensor_data.dim():
                 raise RuntimeError(f"input_rank is {input_rank} but the tensor has {tensor_data.dim()} dimensions")
-            return torch.ops.mctq.fq_lut_tensor(tensor_data, table, K, thr, True, int(channel_axis), float(eps))
-        return torch.ops.mctq.fq_lut_tensor(tensor_data, table, K, thr, False, 0, float(eps))
+            fn = ops._lut_tensor_cuda if direct else torch.ops.mctq.fq_lut_tensor
+            return fn(tensor_data.detach() if direct else tensor_data, table, K, thr, True, int(channel_axis), float(eps))
+        fn = ops._lut_tensor_cuda if direct else torch.ops.mctq.fq_lut_tensor
+        return fn(tensor_data.detach() if direct else tensor_data, table, K, thr, False, 0, float(eps))
     # Python-float threshold: the divisor is formed in double and narrowed once, and half-precision inputs keep
     # their dtype through the normalisation (the reference's eager ops round after each step)
     divisor = float(threshold) + float(eps)
-    return torch.ops.mctq.fq_lut_scalar(tensor_data, table, K, divisor, float(threshold),
-                                        tensor_data.dtype in (torch.bfloat16, torch.float16))
+    fn = ops._lut_scalar_cuda if direct else torch.ops.mctq.fq_lut_scalar
+    return fn(tensor_data, table, K, divisor, float(threshold), tensor_data.dtype in (torch.bfloat16, torch.float16))

@@ -4,7 +4,7 @@ from typing import List
 
 import torch
 
-from mct_quantizers_b200 import ops  # noqa: F401
+from mct_quantizers_b200 import ops
 from mct_quantizers_b200.common.base_inferable_quantizer import mark_quantizer, QuantizationTarget, QuantizerID
 from mct_quantizers_b200.common.constants import ONNX_CUSTOM_OP_DOMAIN
 from mct_quantizers_b200.common.quant_info import QuantizationMethod
@@ -39,6 +39,11 @@ class ActivationSymmetricInferableQuantizer(BaseSymmetricInferableQuantizer):
         if self._use_custom_impl and torch.jit.is_tracing():
             return ActivationSymF.apply(inputs, self.threshold_np, self.signed, self.num_bits)
         # scalar parameters travel by value: one launch on the current stream, no host sync, no autograd graph
+        if ops.direct_ok(inputs):
+            cached = self.__dict__.get('_launch_args')
+            if cached is None or cached[0] != (self.scales, self.zero_points, self.min_quantized_domain, self.max_quantized_domain):
+                cached = self._validated_launch_args(self.scales, self.zero_points)
+            return ops.affine_scalar_direct(inputs, *cached[1])
         return torch.ops.mctq.fq_affine_scalar(inputs.detach(), self.scales, self.zero_points,
                                                self.min_quantized_domain, self.max_quantized_domain)
 

@@ -5,7 +5,7 @@ from typing import List
 import numpy as np
 import torch
 
-from mct_quantizers_b200 import ops  # noqa: F401
+from mct_quantizers_b200 import ops
 from mct_quantizers_b200.common.base_inferable_quantizer import mark_quantizer, QuantizationTarget, QuantizerID
 from mct_quantizers_b200.common.constants import ONNX_CUSTOM_OP_DOMAIN
 from mct_quantizers_b200.common.quant_info import QuantizationMethod
@@ -57,6 +57,11 @@ class ActivationUniformInferableQuantizer(BaseUniformInferableQuantizer):
     def __call__(self, inputs: torch.Tensor):
         if self._use_custom_impl and torch.jit.is_tracing():
             return ActivationUniformF.apply(inputs, self.min_range, self.max_range, self.num_bits)
+        if ops.direct_ok(inputs):
+            cached = self.__dict__.get('_launch_args')
+            if cached is None or cached[0] != (self.scale, self.zero_point, self.min_quantized_domain, self.max_quantized_domain):
+                cached = self._validated_launch_args(self.scale, self.zero_point)
+            return ops.affine_scalar_direct(inputs, *cached[1])
         return torch.ops.mctq.fq_affine_scalar(inputs.detach(), self.scale, self.zero_point,
                                                self.min_quantized_domain, self.max_quantized_domain)
 

@@ -48,6 +48,20 @@ class BasePyTorchInferableQuantizer(BaseInferableQuantizer):
             out.append(hit[1])
         return out
 
+    def _validated_launch_args(self, scale, zero_point):
+        """(key, (scale narrowed to f32, zp, qmin, qmax)) for the per-tensor scalar kernels: validated once (the
+        checks ATen makes on every call) and cached until an attribute changes."""
+        import numpy as np
+        qmin, qmax = int(self.min_quantized_domain), int(self.max_quantized_domain)
+        if qmin > qmax:
+            raise RuntimeError("`quant_min` should be less than or equal to `quant_max`.")
+        if not qmin <= int(zero_point) <= qmax:
+            raise RuntimeError("`zero_point` must be between `quant_min` and `quant_max`.")
+        cached = ((scale, zero_point, self.min_quantized_domain, self.max_quantized_domain),
+                  (float(np.float32(scale)), int(zero_point), qmin, qmax))
+        self.__dict__['_launch_args'] = cached
+        return cached
+
     def __getstate__(self):
         state = dict(self.__dict__)
         state['_per_device'] = {}           # device copies are derived data; do not pickle them

@@ -6,7 +6,7 @@ from typing import List
 import numpy as np
 import torch
 
-from mct_quantizers_b200 import ops  # noqa: F401  (registers torch.ops.mctq)
+from mct_quantizers_b200 import ops
 from mct_quantizers_b200.common.base_inferable_quantizer import mark_quantizer, QuantizationTarget, QuantizerID
 from mct_quantizers_b200.common.constants import ONNX_CUSTOM_OP_DOMAIN
 from mct_quantizers_b200.common.quant_info import QuantizationMethod
@@ -22,6 +22,26 @@ def quantize_sym_weights_torch(input_tensor, num_bits, threshold, per_channel, c
     return export_symmetric(input_tensor, num_bits, threshold, True, per_channel, channel_axis)
 
 
+def _validated_geometry(q, shape, scales, zero_points):
+    """(C, inner, qmin, qmax) after the argument checks torch.fake_quantize_per_{channel,tensor}_affine performs."""
+    qmin, qmax = int(q.min_quantized_domain), int(q.max_quantized_domain)
+    if qmin > qmax:
+        raise RuntimeError("`quant_min` should be less than or equal to `quant_max`.")
+    if q.per_channel:
+        nd = len(shape)
+        axis = q.channel_axis
+        if not -nd <= axis < nd:
+            raise RuntimeError("`axis` must be between 0 and number of dimensions of input")
+        axis %= nd
+        if scales.numel() != shape[axis] or zero_points.numel() != shape[axis]:
+            raise RuntimeError("dimensions of scale and zero-point are not consistent with input tensor")
+        C, inner = ops.contiguous_layout(tuple(shape), axis)
+        return int(C), int(inner), qmin, qmax
+    if scales.numel() != 1 or zero_points.numel() != 1:
+        raise RuntimeError(f"a Tensor with {max(scales.numel(), zero_points.numel())} elements cannot be converted to Scalar")
+    return 1, 1, qmin, qmax
+
+
 def affine_weights_call(q, inputs, export_fn):
     """Shared `__call__` body of the affine weight quantizers (symmetric, POT, uniform):
     reuse cache -> ONNX tracing branch -> one fused kernel on the input's device and current stream.
@@ -34,7 +54,18 @@ def affine_weights_call(q, inputs, export_fn):
     else:
         inputs.requires_grad = False            # same side effect as the reference (raises on non-leaf tensors)
         scales, zero_points = q._on(inputs.device, q.scales, q.zero_points)
-        if q.per_channel:
+        if ops.direct_ok(inputs) and inputs.is_contiguous() and scales.dim() == 1 and scales.dtype == torch.float32 \
+                and zero_points.dtype == torch.int32:
+            # lean path: no dispatcher; the checks ATen repeats on every call are done here once per shape
+            shape = inputs.shape
+            key = (shape, q.channel_axis, q.per_channel, scales.numel(), zero_points.numel(), q.min_quantized_domain, q.max_quantized_domain)
+            geom = q.__dict__.get('_geom')
+            if geom is None or geom[0] != key:
+                geom = (key, _validated_geometry(q, shape, scales, zero_points))
+                q.__dict__['_geom'] = geom
+            C, inner, qmin, qmax = geom[1]
+            outputs = ops.affine_params_direct(inputs.detach(), scales, zero_points, C, inner, qmin, qmax)
+        elif q.per_channel:
             outputs = torch.ops.mctq.fq_affine_channel(inputs, scales.flatten(), zero_points.flatten(), q.channel_axis,
                                                        q.min_quantized_domain, q.max_quantized_domain)
         else:
