@@ -180,20 +180,42 @@ __global__ void __launch_bounds__(kThreads) fq_affine_kernel(const AffineArgs a)
             typename Op::ChanParams p = Op::fetch(sm_par, a.W, slot, a);
 #pragma unroll
             for (int e = 0; e < V; ++e) f[e] = Op::template apply<CODE != 0>(f[e], p, code[e]);
+        } else if (a.inner >= V) {
+            // CH_ELEM, rows at least one vector long: the vector straddles at most one row boundary, so two
+            // parameter sets and a per-element select replace V shared-memory fetches
+            uint32_t slot, rem, k;                  // k = elements of this vector that still belong to the first row
+            if (a.bigrow) {
+                const bool second = l >= win.split;
+                slot = second ? 1u : 0u;
+                rem = 0;
+                k = second ? (uint32_t)V : min((uint32_t)V, win.split - l);
+            } else {
+                locate(l, win, a, slot, rem);
+                k = a.div_inner.d - rem;
+            }
+            const uint32_t slot1 = (slot + 1 == a.W) ? 0u : slot + 1;
+            const typename Op::ChanParams p0 = Op::fetch(sm_par, a.W, slot, a);
+            const typename Op::ChanParams p1 = Op::fetch(sm_par, a.W, slot1, a);
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                const bool first = (uint32_t)e < k;
+                typename Op::ChanParams p;
+                p.inv = first ? p0.inv : p1.inv;
+                p.s = first ? p0.s : p1.s;
+                p.lo = first ? p0.lo : p1.lo;
+                p.hi = first ? p0.hi : p1.hi;
+                p.zp = first ? p0.zp : p1.zp;
+                f[e] = Op::template apply<CODE != 0>(f[e], p, code[e]);
+            }
         } else {
+            // rows shorter than a vector (inner < V, not channel-last): per-element parameter fetch
             uint32_t slot, rem;
             locate(l, win, a, slot, rem);
 #pragma unroll
             for (int e = 0; e < V; ++e) {
-                if (a.bigrow) {
-                    uint32_t jrow = (l + e) >= win.split ? 1u : 0u;
-                    slot = jrow >= a.W ? jrow - a.W : jrow;
-                }
                 typename Op::ChanParams p = Op::fetch(sm_par, a.W, slot, a);
                 f[e] = Op::template apply<CODE != 0>(f[e], p, code[e]);
-                if (!a.bigrow) {
-                    if (++rem == a.div_inner.d) { rem = 0; slot = (slot + 1 == a.W) ? 0 : slot + 1; }
-                }
+                if (++rem == a.div_inner.d) { rem = 0; slot = (slot + 1 == a.W) ? 0 : slot + 1; }
             }
         }
         if (full || (int64_t)l + V <= remaining) {

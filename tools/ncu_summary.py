@@ -70,5 +70,75 @@ def report(path):
         print()
 
 
+def _num(v):
+    try:
+        return float(v.replace(",", ""))
+    except Exception:
+        return float("nan")
+
+
+def _scaled(v, unit, table):
+    return _num(v) * table.get(unit, 1.0)
+
+
+def variants(path, order_path):
+    """One row per captured launch of tools/ncu_targets.py: label and algorithmic GB/s from the order file, the rest
+    from the report."""
+    import json
+    order = json.load(open(order_path))
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    col = {k: hdr.index(k) for k in hdr}
+    t_unit = {"nsecond": 1e-3, "ns": 1e-3, "usecond": 1.0, "us": 1.0, "msecond": 1e3, "ms": 1e3, "second": 1e6}
+    b_unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    print(f"# ncu --set full, one launch per kernel variant ({path})\n")
+    print("`alg GB/s` = algorithmic bytes / gpu__time_duration of the profiled (cold, serialised) launch; `traffic/alg` = "
+          "(dram read + write) / algorithmic bytes.\n")
+    print("| # | variant | kernel | us | alg GB/s | dram R GB | dram W GB | traffic/alg | dram % peak | issue active % | warps active % | regs |")
+    print("|---:|---|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|")
+    data = rows[2:]
+    for i, r in enumerate(data):
+        lab = order[i]["label"] if i < len(order) else "?"
+        alg = order[i]["algorithmic_bytes"] if i < len(order) else float("nan")
+        us = _scaled(r[col["gpu__time_duration.sum"]], units[col["gpu__time_duration.sum"]], t_unit)
+        rd = _scaled(r[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]], b_unit)
+        wr = _scaled(r[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]], b_unit)
+        g = lambda k: r[col[k]] if k in col else ""  # noqa: E731
+        print(f"| {i} | {lab} | `{short(r[col['Kernel Name']])[:60]}` | {us:.1f} | {alg / us / 1e3:.0f} | {rd / 1e9:.3f} | {wr / 1e9:.3f} | "
+              f"{(rd + wr) / alg:.3f} | {_num(g('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed')):.1f} | "
+              f"{_num(g('smsp__issue_active.avg.pct_of_peak_sustained_active')):.1f} | "
+              f"{_num(g('sm__warps_active.avg.pct_of_peak_sustained_active')):.1f} | {g('launch__registers_per_thread')} |")
+
+
+def traffic(path):
+    """Launch list with dram bytes (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum):
+    per-kernel totals as JSON (used for bench.py's roofline.traffic)."""
+    import json
+    with open(path, newline="") as f:
+        lines = [ln for ln in f if ln.startswith('"')]
+    per = OrderedDict()
+    for r in csv.DictReader(io.StringIO("".join(lines))):
+        key = (r["ID"], short(r["Kernel Name"]))
+        d = per.setdefault(key, {})
+        v = _num(r["Metric Value"])
+        unit = r["Metric Unit"]
+        name = r["Metric Name"]
+        if name == "gpu__time_duration.sum":
+            d["us"] = v * {"nsecond": 1e-3, "ns": 1e-3, "usecond": 1.0, "us": 1.0, "msecond": 1e3}.get(unit, 1.0)
+        elif name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            d[name] = v * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
+    agg = OrderedDict()
+    for (_, k), d in per.items():
+        a = agg.setdefault(k, {"launches": 0, "us": 0.0, "dram_read_bytes": 0.0, "dram_write_bytes": 0.0})
+        a["launches"] += 1
+        a["us"] += d.get("us", 0.0)
+        a["dram_read_bytes"] += d.get("dram__bytes_read.sum", 0.0)
+        a["dram_write_bytes"] += d.get("dram__bytes_write.sum", 0.0)
+    for a in agg.values():
+        a["dram_bytes_per_launch"] = (a["dram_read_bytes"] + a["dram_write_bytes"]) / max(a["launches"], 1)
+    print(json.dumps(agg, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "report": report}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "report": report, "variants": variants, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])

@@ -1,0 +1,103 @@
+#!/usr/bin/env python
+"""One launch of every kernel family / variant inside a cudaProfilerStart/Stop range, for an `ncu --set full` capture:
+
+    ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/rNN_variants \
+        python tools/ncu_targets.py [--mb 512]
+    python tools/ncu_summary.py variants gpurun_out/rNN_variants.ncu-rep gpurun_out/rNN_variants_order.json > profiles/rNN_variants.md
+
+The launch order (label, algorithmic bytes) is written next to the report so that the summary can attach the
+algorithmic GB/s to every captured kernel.  Inputs are larger than L2 (default 512 MB per launch).
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mct_quantizers_b200 import _native  # noqa: E402
+from mct_quantizers_b200.pytorch.quantizer_utils import lut_search_table  # noqa: E402
+
+DT = {"f32": (torch.float32, 0, 4), "bf16": (torch.bfloat16, 1, 2)}
+
+
+def vp(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--mb", type=float, default=512.0)
+    ap.add_argument("--order", default="gpurun_out/variants_order.json")
+    args = ap.parse_args()
+    lib = _native.load(build_if_missing=False)
+    dev = torch.device("cuda:0")
+    st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)  # noqa: E731
+    rng = np.random.default_rng(0)
+    lut = np.array(sorted(rng.choice(np.arange(-128, 128), size=16, replace=False)), dtype=np.float32)
+    table_host = lut_search_table(lut, 8, True)
+    table_dev = table_host.to(dev)
+    jobs = []          # (label, algorithmic bytes, callable)
+
+    for dt, (tdt, tag, es) in DT.items():
+        n = int(args.mb * 1e6 / es) // 8192 * 8192
+        x = torch.empty(n, dtype=tdt, device=dev).uniform_(-50, 50)
+        y = torch.empty(n, dtype=tdt, device=dev)
+        yf = torch.empty(n, dtype=torch.float32, device=dev) if es == 2 else y
+        codes = torch.empty(n, dtype=torch.uint8, device=dev)
+        xl = torch.empty(n, dtype=tdt, device=dev).normal_(0, 0.02)
+
+        def add(label, nbytes, fn):
+            jobs.append((f"{label} [{dt}]", int(nbytes), fn))
+
+        add("affine per-tensor scalar qparams (ActivationSymmetric/POT/Uniform)", 2 * n * es,
+            lambda x=x, y=y, n=n, tag=tag: lib.mctq_fq_affine_scalar(vp(x), vp(y), None, n, tag, 0.0129, 77, 0, 255, 0, st()))
+        for (C, inner, label) in ((4096, 11008, "per-channel rows 11008 (CH_VEC)"), (512, 4608, "per-channel conv 512x512x3x3 (CH_VEC)"),
+                                  (960, 9, "per-channel depthwise inner 9 (CH_ELEM)"), (768, 1, "per-channel channel-last C=768 (CH_LAST)")):
+            sc = torch.rand(C, device=dev) * 0.05 + 0.01
+            zp = torch.zeros(C, dtype=torch.int32, device=dev)
+            add(f"affine {label}", 2 * n * es,
+                lambda x=x, y=y, n=n, tag=tag, sc=sc, zp=zp, C=C, inner=inner:
+                lib.mctq_fq_affine(vp(x), vp(y), None, n, tag, vp(sc), vp(zp), C, inner, 0, -128, 127, 0, st()))
+        add("affine per-tensor + int8 codes", n * (2 * es + 1),
+            lambda x=x, y=y, n=n, tag=tag, codes=codes: lib.mctq_fq_affine_scalar(vp(x), vp(y), vp(codes), n, tag, 0.03125, 0, -128, 127, 1, st()))
+        add("affine per-tensor int4 codes only", n * (es + 0.5),
+            lambda x=x, n=n, tag=tag, codes=codes: lib.mctq_fq_affine_scalar(vp(x), None, vp(codes), n, tag, 0.5, 0, -8, 7, 2, st()))
+        for (C, inner, label) in ((4096, 11008, "rows 11008"), (1, 1, "per-tensor")):
+            thr = torch.rand(C, device=dev) * 0.05 + 0.06
+            nb = lib.mctq_lut_prepared_bytes(16, 8, 1, C)
+            blob = torch.empty(nb, dtype=torch.uint8, device=dev)
+            rc = lib.mctq_lut_prepare(vp(table_host), 16, vp(thr), C, 1e-8, 0, 1.0, 1.0, 0, vp(blob), nb, st())
+            assert rc == 0, rc
+            add(f"lut-prepared K=16 {label}", n * (es + 4),
+                lambda xl=xl, yf=yf, n=n, tag=tag, blob=blob, C=C, inner=inner:
+                lib.mctq_fq_lut_prepared(vp(xl), vp(yf), None, n, tag, vp(blob), 16, 8, 1, C, inner, 0, 0, st()))
+            if C > 1:
+                add(f"lut-prepared K=16 {label} + int4 indices", n * (es + 4.5),
+                    lambda xl=xl, yf=yf, n=n, tag=tag, blob=blob, C=C, inner=inner, codes=codes:
+                    lib.mctq_fq_lut_prepared(vp(xl), vp(yf), vp(codes), n, tag, vp(blob), 16, 8, 1, C, inner, 0, 2, st()))
+                add(f"lut generic (search loop) K=16 {label}", n * (es + 4),
+                    lambda xl=xl, yf=yf, n=n, tag=tag, thr=thr, C=C, inner=inner:
+                    lib.mctq_fq_lut(vp(xl), vp(yf), None, n, tag, vp(table_dev), 16, vp(thr), C, inner, 0, 1e-8, 0, st()))
+
+    torch.cuda.synchronize()
+    for _, _, fn in jobs:          # warm-up (module load, shared-memory attributes) outside the profiled range
+        rc = fn()
+        assert rc == 0, rc
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    for _, _, fn in jobs:
+        fn()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+    os.makedirs(os.path.dirname(args.order) or ".", exist_ok=True)
+    with open(args.order, "w") as f:
+        json.dump([{"label": lab, "algorithmic_bytes": nb} for lab, nb, _ in jobs], f, indent=1)
+    print(f"{len(jobs)} launches profiled")
+
+
+if __name__ == "__main__":
+    main()
