@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(kThreads) fq_lutp_kernel(const LutPArgs a) {
     constexpr uint32_t TILE = kThreads * UNROLL * V;
     extern __shared__ __align__(16) float sm_dyn[];                   // [records W * rec_floats][cells NC + 1 (+pad)][orig P]
     __shared__ Window sm_win;
-    __shared__ uint32_t sm_c0;
+    __shared__ __align__(8) uint64_t sm_bar;
 
     const uint32_t tid = threadIdx.x;
     const int64_t t0 = (int64_t)blockIdx.x * TILE;
@@ -183,51 +183,40 @@ __global__ void __launch_bounds__(kThreads) fq_lutp_kernel(const LutPArgs a) {
         }
     }
 
+    // Stage the decision tables with the bulk-copy engine (1-D TMA): the blob already holds them in the layout the
+    // CTA wants -- [cells | orig] contiguous and channel records back to back -- so one elected thread arms the
+    // mbarrier and issues at most three cp.async.bulk copies (cells + orig, records c0 .. C-1, wrapped records 0 ..);
+    // they complete while every thread's streaming loads of the data tile are in flight.
     const uint32_t Wn = CHMODE == CH_PT ? 1u : a.W;
     float* sm_rec = sm_dyn;
     uint8_t* sm_cells = reinterpret_cast<uint8_t*>(sm_dyn + (size_t)Wn * a.rec_floats);
     uint8_t* sm_orig = sm_cells + ((a.NC + 1 + 15) & ~15);
-    {
-        // channel-independent tables: cells (NC + 1 bytes) and original indices (P bytes), copied as 32-bit words
-        const uint32_t* gc = reinterpret_cast<const uint32_t*>(a.blob + a.off_cells);
-        uint32_t* sc = reinterpret_cast<uint32_t*>(sm_cells);
-        const int words = ((a.NC + 1 + 15) & ~15) / 4;
-        for (int i = tid; i < words; i += kThreads) sc[i] = __ldg(gc + i);
-        if (CODE != 0) {
-            const uint32_t* go = reinterpret_cast<const uint32_t*>(a.blob + a.off_orig);
-            uint32_t* so = reinterpret_cast<uint32_t*>(sm_orig);
-            for (int i = tid; i < (a.P + 3) / 4; i += kThreads) so[i] = __ldg(go + i);
-        }
-    }
-    if (CHMODE == CH_PT) {
-        const float* g = reinterpret_cast<const float*>(a.blob + a.off_rec);
-        for (int k = tid; k < a.rec_floats; k += kThreads) sm_rec[k] = __ldg(g + k);
-    } else {
-        if (tid == 0) {
-            int64_t g0 = a.elem_offset + t0;
-            int64_t r0 = g0 / a.inner;
-            int64_t off = g0 - r0 * a.inner;
+    if (tid == 0) {
+        mbar_init(&sm_bar, 1);
+        uint32_t c0 = 0;
+        if (CHMODE != CH_PT) {
+            const int64_t g0 = a.elem_offset + t0;
+            const int64_t r0 = g0 / a.inner;
+            const int64_t off = g0 - r0 * a.inner;
             Window wv;
             wv.off0 = a.bigrow ? 0u : (uint32_t)off;
-            int64_t sp = a.inner - off;
+            const int64_t sp = a.inner - off;
             wv.split = (uint32_t)(sp > (int64_t)TILE ? (int64_t)TILE + 1 : sp);
-            sm_c0 = (uint32_t)(r0 % a.C);
             sm_win = wv;
+            c0 = (uint32_t)(r0 % a.C);
         }
-        __syncthreads();
-        const uint32_t c0 = sm_c0;
-        const uint32_t total = a.W * (uint32_t)a.rec_floats;
-        const float* grec = reinterpret_cast<const float*>(a.blob + a.off_rec);
-        for (uint32_t i = tid; i < total; i += kThreads) {
-            uint32_t slot = i / (uint32_t)a.rec_floats, k = i - slot * (uint32_t)a.rec_floats;
-            uint64_t c = (uint64_t)c0 + slot;
-            c = c % (uint64_t)a.C;
-            sm_rec[i] = __ldg(grec + c * a.rec_floats + k);
-        }
+        const uint32_t rec_bytes = (uint32_t)a.rec_floats * 4u;
+        const uint32_t tab_bytes = (uint32_t)(a.off_rec - a.off_cells);
+        const uint32_t n1 = min(Wn, (uint32_t)a.C - c0);            // records before the channel index wraps
+        mbar_arrive_expect_tx(&sm_bar, tab_bytes + Wn * rec_bytes);
+        bulk_g2s(sm_cells, a.blob + a.off_cells, tab_bytes, &sm_bar);
+        bulk_g2s(sm_rec, a.blob + a.off_rec + (size_t)c0 * rec_bytes, n1 * rec_bytes, &sm_bar);
+        if (n1 < Wn) bulk_g2s(reinterpret_cast<char*>(sm_rec) + (size_t)n1 * rec_bytes, a.blob + a.off_rec, (Wn - n1) * rec_bytes, &sm_bar);
     }
-    __syncthreads();
+    __syncthreads();                                                  // barrier init + window visible to everyone
     Window win;
     if (CHMODE != CH_PT) win = sm_win;
+    mbar_wait(&sm_bar, 0);
 
     const float NCf = (float)a.NC;
     const uint32_t rec_bytes = (uint32_t)a.rec_floats * 4u;
@@ -245,26 +234,50 @@ __global__ void __launch_bounds__(kThreads) fq_lutp_kernel(const LutPArgs a) {
         const char* rec = rec_base + slot * rec_bytes;
         float sp = *reinterpret_cast<const float*>(rec + 2 * ybytes);
         const float nan_probe = (f[0] + f[1]) + (f[2] + f[3]);     // NaN iff some element is NaN (or inf - inf)
-#pragma unroll
-        for (int e = 0; e < V; ++e) {
-            if (CHMODE == CH_ELEM) {
-                if (a.bigrow) {
-                    uint32_t jrow = (l + e) >= win.split ? 1u : 0u;
-                    slot = jrow >= a.W ? jrow - a.W : jrow;
-                }
+        // CH_ELEM: a vector of 4 straddles row boundaries.  Rows of at least 4 elements: at most one boundary, so the
+        // record pointer / cell scale of the second row are selected per element; shorter rows advance per element.
+        const bool two_rows = CHMODE == CH_ELEM && a.inner >= V;
+        uint32_t k = V;                                             // elements of this vector in the first row
+        const char* rec1 = rec;
+        float sp1 = sp;
+        if (two_rows) {
+            if (a.bigrow) {
+                const bool second = l >= win.split;
+                slot = second ? 1u : 0u;
                 rec = rec_base + slot * rec_bytes;
                 sp = *reinterpret_cast<const float*>(rec + 2 * ybytes);
+                k = second ? (uint32_t)V : min((uint32_t)V, win.split - l);
+            } else {
+                k = a.div_inner.d - rem;
+            }
+            const uint32_t slot1 = (slot + 1 == a.W) ? 0u : slot + 1;
+            rec1 = rec_base + slot1 * rec_bytes;
+            sp1 = *reinterpret_cast<const float*>(rec1 + 2 * ybytes);
+        }
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            const char* r = rec;
+            float s = sp;
+            if (CHMODE == CH_ELEM) {
+                if (two_rows) {
+                    const bool first = (uint32_t)e < k;
+                    r = first ? rec : rec1;
+                    s = first ? sp : sp1;
+                } else {
+                    r = rec_base + slot * rec_bytes;
+                    s = *reinterpret_cast<const float*>(r + 2 * ybytes);
+                }
             }
             const float x = f[e];
-            const float u = fma_sat(x, sp, 0.5f);                       // saturates to [0, 1]; NaN -> 0
+            const float u = fma_sat(x, s, 0.5f);                        // saturates to [0, 1]; NaN -> 0
             const float cf = __fmaf_rn(u, NCf, kMagicRound);            // integer cell index in the low mantissa bits
             const uint32_t cell = __float_as_uint(cf) & 0x1fffu;
             const uint32_t b4 = (uint32_t)sm_cells[cell] << 2;          // byte offset of the candidate threshold
-            const float X = *reinterpret_cast<const float*>(rec + b4);
+            const float X = *reinterpret_cast<const float*>(r + b4);
             const uint32_t p4 = b4 + ((x > X) ? 4u : 0u);
-            f[e] = *reinterpret_cast<const float*>(rec + ybytes + p4);
+            f[e] = *reinterpret_cast<const float*>(r + ybytes + p4);
             if (CODE != 0) code[e] = sm_orig[p4 >> 2];
-            if (CHMODE == CH_ELEM && !a.bigrow) {
+            if (CHMODE == CH_ELEM && !two_rows) {
                 if (++rem == a.div_inner.d) { rem = 0; slot = (slot + 1 == a.W) ? 0 : slot + 1; }
             }
         }
@@ -443,6 +456,7 @@ int mctq_fq_lut_prepared(const void* x, float* y, void* idx, int64_t n, int x_dt
     const size_t esz = x_dtype == MCTQ_F32 ? 4 : 2;
     bool vec_ok = (reinterpret_cast<uintptr_t>(x) % (4 * esz)) == 0 && (!y || aligned16(y));
     if (idx_mode != MCTQ_CODES_NONE) vec_ok = vec_ok && (reinterpret_cast<uintptr_t>(idx) & 3u) == 0;
+    if (!aligned16(prepared_dev)) vec_ok = false;  // the tables are staged with 16-byte bulk copies
     if (!vec_ok) return MCTQ_E_BADARG;             // caller uses the generic entry point for misaligned views
     LutPArgs a;
     memset(&a, 0, sizeof(a));
