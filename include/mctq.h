@@ -85,6 +85,33 @@ int mctq_fq_affine(const void* x, void* y, void* codes, int64_t n, int x_dtype,
 int mctq_fq_affine_scalar(const void* x, void* y, void* codes, int64_t n, int x_dtype,
                           float scale, int32_t zp, int32_t qmin, int32_t qmax, int code_mode, void* stream);
 
+/* Prepared per-channel parameters (the fast path for per-channel weights): mctq_affine_prepare turns scale[C] / zp[C]
+ * into a device blob holding, per channel, the record {1/s, s, zp, (float)zp} plus the same values as three arrays; the
+ * kernels launched by mctq_fq_affine_prepared stage the channel window of every tile from that blob with 1-D TMA bulk
+ * copies (cp.async.bulk + mbarrier) instead of per-thread load / divide / store loops.  Same reference call sites and
+ * arithmetic as mctq_fq_affine (1/s is the same IEEE f32 reciprocal, computed once).  Neither call synchronises.
+ *   prepared_dev   DEVICE buffer, 16-byte aligned, >= mctq_affine_prepared_bytes(C) bytes; valid for as long as
+ *                  scale / zp do not change */
+size_t mctq_affine_prepared_bytes(int64_t C);
+int mctq_affine_prepare(const float* scale, const int32_t* zp, int64_t C, void* prepared_dev, size_t prepared_bytes,
+                        void* stream);
+int mctq_fq_affine_prepared(const void* x, void* y, void* codes, int64_t n, int x_dtype, const void* prepared_dev,
+                            int64_t C, int64_t inner, int64_t elem_offset, int32_t qmin, int32_t qmax, int code_mode,
+                            void* stream);
+
+/* Per-tensor affine fake-quant fused with the elementwise producer of the activation.
+ * Replaces the pair  <producer>(x[, x2]) -> PytorchActivationQuantizationHolder.forward
+ *   (mct_quantizers/pytorch/activation_quantization_holder.py:43-53 after a ReLU / ReLU6 / residual add of the exported
+ *   model) with ONE kernel: the intermediate activation is never written to HBM.  Bit-identical to the eager
+ *   composition (producer evaluated in f32 and rounded to x_dtype, then the recipe of mctq_fq_affine_scalar).
+ * x2 is read only by the ADD flavours (same dtype and length as x). */
+#define MCTQ_PRE_RELU 1      /* y = fq(max(x, 0))        */
+#define MCTQ_PRE_RELU6 2     /* y = fq(min(max(x, 0), 6)) */
+#define MCTQ_PRE_ADD 3       /* y = fq(x + x2)           */
+#define MCTQ_PRE_ADD_RELU 4  /* y = fq(max(x + x2, 0))   */
+int mctq_fq_affine_scalar_pre(const void* x, const void* x2, void* y, int64_t n, int x_dtype, int pre_op, float scale,
+                              int32_t zp, int32_t qmin, int32_t qmax, void* stream);
+
 /* Dequantise codes written by the functions above: y = (q - zp) * s  (f32 out).  No reference call site:
  * this is the consumer side of the code wire format. */
 int mctq_dequant_affine(const void* codes, int code_mode, int is_signed, float* y, int64_t n,

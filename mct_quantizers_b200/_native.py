@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libmctq_sm100.so")
 
 F32, BF16, F16 = 0, 1, 2
 CODES_NONE, CODES_INT8, CODES_INT4 = 0, 1, 2
+PRE_RELU, PRE_RELU6, PRE_ADD, PRE_ADD_RELU = 1, 2, 3, 4
 
 _lock = threading.Lock()
 _lib = None
@@ -34,6 +35,10 @@ SIGNATURES = {
     "mctq_build_info": (ctypes.c_char_p, []),
     "mctq_fq_affine": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_i64, c_i64, c_i32, c_i32, c_int, c_vp]),
     "mctq_fq_affine_scalar": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_f32, c_i32, c_i32, c_i32, c_int, c_vp]),
+    "mctq_affine_prepared_bytes": (c_sz, [c_i64]),
+    "mctq_affine_prepare": (c_int, [c_vp, c_vp, c_i64, c_vp, c_sz, c_vp]),
+    "mctq_fq_affine_prepared": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_i64, c_i64, c_i64, c_i32, c_i32, c_int, c_vp]),
+    "mctq_fq_affine_scalar_pre": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_f32, c_i32, c_i32, c_i32, c_vp]),
     "mctq_dequant_affine": (c_int, [c_vp, c_int, c_int, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp]),
     "mctq_multi_tile_elems": (c_i64, []),
     "mctq_multi_plan": (c_i64, [c_vp, c_int, c_vp]),

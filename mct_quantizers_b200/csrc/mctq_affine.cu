@@ -25,7 +25,16 @@ struct AffineArgs {
     // pattern, so that every aligned vector of V elements reads V consecutive entries
     uint32_t period;
     FastDiv div_period;
+    // prepared parameters (mctq_affine_prepare): records {1/s, s, zp bits, (float)zp} per channel and the same values as
+    // three arrays [inv | s | zp] of C4 = roundup(C, 4) entries each; NULL for the raw-parameter entry points
+    const float4* prep_rec;
+    const float* prep_soa;
+    const int32_t* prep_flags;   // [0] != 0: some zero point is non-zero
+    int64_t C4;
 };
+
+constexpr size_t kPrepHeaderBytes = 16;
+inline size_t prep_bytes(int64_t C) { int64_t C4 = (C + 3) & ~(int64_t)3; return kPrepHeaderBytes + (size_t)C * 16 + (size_t)C4 * 12; }
 
 template <bool RINT> struct AffineOp {
     using Args = AffineArgs;
@@ -61,6 +70,18 @@ template <bool RINT> struct AffineOp {
         else { p.lo = (float)(a.qmin - p.zp); p.hi = (float)(a.qmax - p.zp); }
         return p;
     }
+    // prepared record {1/s, s, zp bits, (float)zp}: one 16-byte shared-memory load, no int -> float conversions
+    // ((float)(qmin - zp) == (float)qmin - (float)zp exactly: all three are integers below 2^24)
+    __device__ static __forceinline__ ChanParams fetch_rec(const float* sm, uint32_t slot, const Args& a) {
+        const float4 r = reinterpret_cast<const float4*>(sm)[slot];
+        ChanParams p;
+        p.inv = r.x;
+        p.s = r.y;
+        p.zp = __float_as_int(r.z);
+        if (RINT) { p.lo = (float)a.qmin; p.hi = (float)a.qmax; }
+        else { p.lo = __fsub_rn((float)a.qmin, r.w); p.hi = __fsub_rn((float)a.qmax, r.w); }
+        return p;
+    }
     // returns y; code receives the clamped integer q
     template <bool WANT_CODE>
     __device__ static __forceinline__ float apply(float x, const ChanParams& p, int& code) {
@@ -85,7 +106,10 @@ template <bool RINT> struct AffineOp {
 };
 
 // ------------------------------------------------------------------------------------------ affine kernel
-template <typename T, int CHMODE, int CODE, int UNROLL, bool RINT>
+// PREP: the per-channel parameters come from a prepared blob and are staged with 1-D TMA bulk copies (one elected thread,
+// one mbarrier) instead of per-thread load / divide / store loops -- the staging cost of a tile that touches hundreds
+// of channels (short rows, channel-innermost layouts) drops to a handful of instructions.
+template <typename T, int CHMODE, int CODE, int UNROLL, bool RINT, bool PREP>
 __global__ void __launch_bounds__(kThreads) fq_affine_kernel(const AffineArgs a) {
     using Op = AffineOp<RINT>;
     constexpr int V = 16 / sizeof(T);
@@ -93,6 +117,7 @@ __global__ void __launch_bounds__(kThreads) fq_affine_kernel(const AffineArgs a)
     constexpr uint32_t TILE = kThreads * UNROLL * V;
     extern __shared__ __align__(16) float sm_par[];
     __shared__ Window sm_win;
+    __shared__ __align__(8) uint64_t sm_bar;
 
     const uint32_t tid = threadIdx.x;
     const int64_t t0 = (int64_t)blockIdx.x * TILE;
@@ -126,6 +151,39 @@ __global__ void __launch_bounds__(kThreads) fq_affine_kernel(const AffineArgs a)
     bool has_zp = true;
     if (CHMODE == CH_PT) {
         pu = Op::uniform(a);
+    } else if (PREP) {
+        if (tid == 0) {
+            mbar_init(&sm_bar, 1);
+            if (CHMODE == CH_LAST) {
+                // period / C back-to-back copies of each parameter array: entry i = channel i % C
+                const uint32_t Cb = (uint32_t)a.C * 4u, reps = a.period / (uint32_t)a.C;
+                mbar_arrive_expect_tx(&sm_bar, 3u * a.period * 4u);
+                for (uint32_t arr = 0; arr < 3; ++arr)
+                    for (uint32_t r = 0; r < reps; ++r)
+                        bulk_g2s(sm_par + arr * a.period + r * (uint32_t)a.C, a.prep_soa + arr * a.C4, Cb, &sm_bar);
+            } else {
+                const int64_t g0 = a.elem_offset + t0;
+                const int64_t r0 = g0 / a.inner;
+                const int64_t off = g0 - r0 * a.inner;
+                Window wv;
+                wv.off0 = a.bigrow ? 0u : (uint32_t)off;
+                const int64_t sp = a.inner - off;
+                wv.split = (uint32_t)(sp > (int64_t)TILE ? (int64_t)TILE + 1 : sp);
+                sm_win = wv;
+                const uint32_t c0 = (uint32_t)(r0 % a.C);
+                const uint32_t n1 = min(a.W, (uint32_t)a.C - c0);          // records before the channel index wraps
+                mbar_arrive_expect_tx(&sm_bar, a.W * 16u);
+                bulk_g2s(sm_par, a.prep_rec + c0, n1 * 16u, &sm_bar);
+                if (n1 < a.W) bulk_g2s(sm_par + 4u * n1, a.prep_rec, (a.W - n1) * 16u, &sm_bar);
+            }
+        }
+        if (CHMODE == CH_LAST) {
+            base_mod = (uint32_t)((uint64_t)(a.elem_offset + t0) % a.period);
+            has_zp = __ldg(a.prep_flags) != 0;
+        }
+        __syncthreads();                                               // barrier init + window visible to everyone
+        if (CHMODE != CH_LAST) win = sm_win;
+        mbar_wait(&sm_bar, 0);
     } else if (CHMODE == CH_LAST) {
         // entry i of the period holds the parameters of channel i % C (struct of arrays: inv | s | zp)
         int any_zp = 0;
@@ -177,7 +235,7 @@ __global__ void __launch_bounds__(kThreads) fq_affine_kernel(const AffineArgs a)
         } else if (CHMODE == CH_VEC) {
             uint32_t slot, rem;
             locate(l, win, a, slot, rem);
-            typename Op::ChanParams p = Op::fetch(sm_par, a.W, slot, a);
+            typename Op::ChanParams p = PREP ? Op::fetch_rec(sm_par, slot, a) : Op::fetch(sm_par, a.W, slot, a);
 #pragma unroll
             for (int e = 0; e < V; ++e) f[e] = Op::template apply<CODE != 0>(f[e], p, code[e]);
         } else if (a.inner >= V) {
@@ -194,8 +252,8 @@ __global__ void __launch_bounds__(kThreads) fq_affine_kernel(const AffineArgs a)
                 k = a.div_inner.d - rem;
             }
             const uint32_t slot1 = (slot + 1 == a.W) ? 0u : slot + 1;
-            const typename Op::ChanParams p0 = Op::fetch(sm_par, a.W, slot, a);
-            const typename Op::ChanParams p1 = Op::fetch(sm_par, a.W, slot1, a);
+            const typename Op::ChanParams p0 = PREP ? Op::fetch_rec(sm_par, slot, a) : Op::fetch(sm_par, a.W, slot, a);
+            const typename Op::ChanParams p1 = PREP ? Op::fetch_rec(sm_par, slot1, a) : Op::fetch(sm_par, a.W, slot1, a);
 #pragma unroll
             for (int e = 0; e < V; ++e) {
                 const bool first = (uint32_t)e < k;
@@ -213,7 +271,7 @@ __global__ void __launch_bounds__(kThreads) fq_affine_kernel(const AffineArgs a)
             locate(l, win, a, slot, rem);
 #pragma unroll
             for (int e = 0; e < V; ++e) {
-                typename Op::ChanParams p = Op::fetch(sm_par, a.W, slot, a);
+                typename Op::ChanParams p = PREP ? Op::fetch_rec(sm_par, slot, a) : Op::fetch(sm_par, a.W, slot, a);
                 f[e] = Op::template apply<CODE != 0>(f[e], p, code[e]);
                 if (++rem == a.div_inner.d) { rem = 0; slot = (slot + 1 == a.W) ? 0 : slot + 1; }
             }
@@ -239,6 +297,26 @@ __global__ void __launch_bounds__(kThreads) fq_affine_kernel(const AffineArgs a)
                 }
             }
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ parameter preparation
+// blob = [16-byte header: int32 any_nonzero_zp][records float4 x C][inv C4 | s C4 | zp C4]
+__global__ void __launch_bounds__(kThreads) affine_prepare_kernel(const float* __restrict__ scale, const int32_t* __restrict__ zp,
+                                                                  int64_t C, int64_t C4, uint8_t* blob) {
+    int32_t* flags = reinterpret_cast<int32_t*>(blob);
+    float4* rec = reinterpret_cast<float4*>(blob + kPrepHeaderBytes);
+    float* soa = reinterpret_cast<float*>(blob + kPrepHeaderBytes + (size_t)C * 16);
+    for (int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x; c < C4; c += (int64_t)gridDim.x * kThreads) {
+        float s = 1.0f;
+        int z = 0;
+        if (c < C) { s = scale[c]; z = zp[c]; }
+        const float inv = __fdiv_rn(1.0f, s);
+        if (c < C) rec[c] = make_float4(inv, s, __int_as_float(z), (float)z);
+        soa[c] = inv;
+        soa[C4 + c] = s;
+        soa[2 * C4 + c] = __int_as_float(z);
+        if (z != 0) atomicOr(flags, 1);
     }
 }
 
@@ -354,7 +432,7 @@ int check_codes(int32_t qmin, int32_t qmax, int code_mode, const void* codes) {
     return MCTQ_E_BADARG;
 }
 
-template <typename T, int CHMODE, int CODE, int UNROLL, bool RINT>
+template <typename T, int CHMODE, int CODE, int UNROLL, bool RINT, bool PREP = false>
 int launch_affine_tiles(const AffineArgs& a_in, cudaStream_t st) {
     constexpr int V = 16 / sizeof(T);
     constexpr uint32_t TILE = kThreads * UNROLL * V;
@@ -364,17 +442,27 @@ int launch_affine_tiles(const AffineArgs& a_in, cudaStream_t st) {
         a.div_W = make_fastdiv((uint32_t)a.C);
         a.div_period = make_fastdiv(a.period);
         smem = (size_t)a.period * 3 * sizeof(float);
-        int rc = ensure_smem(fq_affine_kernel<T, CHMODE, CODE, UNROLL, RINT>, smem);
+        int rc = ensure_smem(fq_affine_kernel<T, CHMODE, CODE, UNROLL, RINT, PREP>, smem);
         if (rc) return rc;
     } else if (CHMODE != CH_PT) {
         set_window(a, TILE);
-        smem = (size_t)a.W * 3 * sizeof(float);
-        int rc = ensure_smem(fq_affine_kernel<T, CHMODE, CODE, UNROLL, RINT>, smem);
+        smem = (size_t)a.W * (PREP ? 4 : 3) * sizeof(float);
+        int rc = ensure_smem(fq_affine_kernel<T, CHMODE, CODE, UNROLL, RINT, PREP>, smem);
         if (rc) return rc;
     }
     int64_t tiles = (a.n + TILE - 1) / TILE;
     if (tiles > 0x7fffffffLL) return MCTQ_E_BADARG;
-    return launch_streaming(fq_affine_kernel<T, CHMODE, CODE, UNROLL, RINT>, (unsigned)tiles, smem, st, a);
+    return launch_streaming(fq_affine_kernel<T, CHMODE, CODE, UNROLL, RINT, PREP>, (unsigned)tiles, smem, st, a);
+}
+
+// prepared parameters: TMA-staged variants (fast range, unroll 4, every code mode)
+template <typename T, int CHMODE>
+int launch_affine_prepared(const AffineArgs& a, int code_mode, cudaStream_t st) {
+    switch (code_mode) {
+        case MCTQ_CODES_INT8: return launch_affine_tiles<T, CHMODE, MCTQ_CODES_INT8, 4, false, true>(a, st);
+        case MCTQ_CODES_INT4: return launch_affine_tiles<T, CHMODE, MCTQ_CODES_INT4, 4, false, true>(a, st);
+        default: return launch_affine_tiles<T, CHMODE, MCTQ_CODES_NONE, 4, false, true>(a, st);
+    }
 }
 
 template <typename T, int CHMODE, int CODE, bool RINT>
@@ -426,6 +514,12 @@ int launch_affine_typed(const AffineArgs& a, int code_mode, cudaStream_t st) {
             if (period <= 4096) { chmode = CH_LAST; a2.period = (uint32_t)period; }
         }
     }
+    if (a.prep_rec && !rint_path && g_unroll == 4) {
+        // prepared blob: bulk-copy staging needs 16-byte granules (CH_LAST: whole arrays of C floats)
+        if (chmode == CH_VEC) return launch_affine_prepared<T, CH_VEC>(a2, code_mode, st);
+        if (chmode == CH_ELEM) return launch_affine_prepared<T, CH_ELEM>(a2, code_mode, st);
+        if (chmode == CH_LAST && a.C % 4 == 0) return launch_affine_prepared<T, CH_LAST>(a2, code_mode, st);
+    }
 #define MCTQ_DISPATCH_AFF(CM)                                                                   \
     return rint_path ? launch_affine_code<T, CM, true>(a2, code_mode, st) : launch_affine_code<T, CM, false>(a2, code_mode, st)
     if (chmode == CH_PT) { MCTQ_DISPATCH_AFF(CH_PT); }
@@ -461,6 +555,39 @@ int mctq_fq_affine(const void* x, void* y, void* codes, int64_t n, int x_dtype, 
     AffineArgs a;
     memset(&a, 0, sizeof(a));
     a.x = x; a.y = y; a.codes = codes; a.n = n; a.scale = scale; a.zp = zp;
+    a.C = C; a.inner = C == 1 ? 1 : inner; a.elem_offset = C == 1 ? 0 : elem_offset; a.qmin = qmin; a.qmax = qmax;
+    return launch_affine(a, x_dtype, code_mode, (cudaStream_t)stream);
+}
+
+size_t mctq_affine_prepared_bytes(int64_t C) { return C < 1 ? 0 : prep_bytes(C); }
+
+int mctq_affine_prepare(const float* scale, const int32_t* zp, int64_t C, void* prepared_dev, size_t prepared_bytes, void* stream) {
+    if (!scale || !zp || !prepared_dev || C < 1 || prepared_bytes < prep_bytes(C) || !aligned16(prepared_dev)) return MCTQ_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(prepared_dev, 0, kPrepHeaderBytes, st);
+    if (e != cudaSuccess) return (int)e;
+    const int64_t C4 = (C + 3) & ~(int64_t)3;
+    int64_t blocks = (C4 + kThreads - 1) / kThreads;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    affine_prepare_kernel<<<(unsigned)blocks, kThreads, 0, st>>>(scale, zp, C, C4, reinterpret_cast<uint8_t*>(prepared_dev));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cuda_rc(cudaGetLastError());
+}
+
+int mctq_fq_affine_prepared(const void* x, void* y, void* codes, int64_t n, int x_dtype, const void* prepared_dev, int64_t C,
+                            int64_t inner, int64_t elem_offset, int32_t qmin, int32_t qmax, int code_mode, void* stream) {
+    if (!prepared_dev || C < 1 || !aligned16(prepared_dev)) return MCTQ_E_BADARG;
+    const uint8_t* blob = reinterpret_cast<const uint8_t*>(prepared_dev);
+    AffineArgs a;
+    memset(&a, 0, sizeof(a));
+    a.C4 = (C + 3) & ~(int64_t)3;
+    a.prep_flags = reinterpret_cast<const int32_t*>(blob);
+    a.prep_rec = reinterpret_cast<const float4*>(blob + kPrepHeaderBytes);
+    a.prep_soa = reinterpret_cast<const float*>(blob + kPrepHeaderBytes + (size_t)C * 16);
+    // the arrays inside the blob double as the raw parameters for the variants that do not use bulk staging
+    a.scale = a.prep_soa + a.C4;
+    a.zp = reinterpret_cast<const int32_t*>(a.prep_soa + 2 * a.C4);
+    a.x = x; a.y = y; a.codes = codes; a.n = n;
     a.C = C; a.inner = C == 1 ? 1 : inner; a.elem_offset = C == 1 ? 0 : elem_offset; a.qmin = qmin; a.qmax = qmax;
     return launch_affine(a, x_dtype, code_mode, (cudaStream_t)stream);
 }

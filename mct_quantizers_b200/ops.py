@@ -25,6 +25,7 @@ _DT = {torch.float32: _native.F32, torch.bfloat16: _native.BF16, torch.float16: 
 
 _LIB = torch.library.Library("mctq", "DEF")
 _LIB.define("fq_affine_scalar(Tensor x, float scale, int zero_point, int quant_min, int quant_max) -> Tensor")
+_LIB.define("fq_affine_scalar_pre(Tensor x, Tensor? other, int pre_op, float scale, int zero_point, int quant_min, int quant_max) -> Tensor")
 _LIB.define("fq_affine_tensor(Tensor x, Tensor scale, Tensor zero_point, int quant_min, int quant_max) -> Tensor")
 _LIB.define("fq_affine_channel(Tensor x, Tensor scale, Tensor zero_point, int axis, int quant_min, int quant_max) -> Tensor")
 _LIB.define("fq_lut_tensor(Tensor x, Tensor table, int K, Tensor threshold, bool per_channel, int axis, float eps) -> Tensor")
@@ -84,6 +85,7 @@ class _on_device:
         self.prev = _get_device() if _get_device is not None else torch.cuda.current_device()
         if self.prev != self.idx:
             torch.cuda.set_device(self.idx)
+        return self
 
     def __exit__(self, *exc):
         if self.prev != self.idx:
@@ -216,6 +218,100 @@ def _affine_scalar_cuda(x, scale, zero_point, quant_min, quant_max):
     return affine_scalar_direct(x, float(np.float32(scale)), int(zero_point), int(quant_min), int(quant_max))
 
 
+def affine_scalar_pre_direct(x, other, pre_op, scale_f32, zero_point, quant_min, quant_max):
+    """Producer (relu / relu6 / add / add+relu) and per-tensor fake-quant in ONE kernel: mctq_fq_affine_scalar_pre.
+    Lean launch; arguments are already validated."""
+    tag = _DT.get(x.dtype)
+    if tag is None:
+        _dtype_tag(x)
+    xd = x if x.is_contiguous() else _dense(x)
+    od = None
+    if pre_op in (_native.PRE_ADD, _native.PRE_ADD_RELU):
+        if other is None or other.shape != x.shape or other.dtype != x.dtype or other.device != x.device:
+            raise RuntimeError("fused add needs a second tensor of the same shape, dtype and device (no broadcasting)")
+        od = other if other.stride() == xd.stride() and _is_dense_permutation(other) else None
+        if od is None:
+            od = other.contiguous()
+            if not xd.is_contiguous():
+                xd = xd.contiguous()
+    y = torch.empty_like(xd)
+    n = xd.numel()
+    if n:
+        lib = _native._lib or _native.load()
+        index = xd.device.index
+        prev = _get_device()
+        if prev != index:
+            _set_device(index)
+        rc = lib.mctq_fq_affine_scalar_pre(xd.data_ptr(), od.data_ptr() if od is not None else None, y.data_ptr(), n, tag,
+                                           pre_op, scale_f32, zero_point, quant_min, quant_max, _raw_stream(index))
+        if prev != index:
+            _set_device(prev)
+        if rc:
+            _native.check(rc, "mctq_fq_affine_scalar_pre")
+    return y
+
+
+def _affine_scalar_pre_cuda(x, other, pre_op, scale, zero_point, quant_min, quant_max):
+    _dtype_tag(x)
+    _check_range(quant_min, quant_max)
+    if not quant_min <= zero_point <= quant_max:
+        raise RuntimeError("`zero_point` must be between `quant_min` and `quant_max`.")
+    if pre_op not in (_native.PRE_RELU, _native.PRE_RELU6, _native.PRE_ADD, _native.PRE_ADD_RELU):
+        raise RuntimeError("pre_op must be 1 (relu), 2 (relu6), 3 (add) or 4 (add + relu)")
+    if pre_op in (_native.PRE_ADD, _native.PRE_ADD_RELU) and (other is None or other.shape != x.shape or other.dtype != x.dtype
+                                                              or other.device != x.device):
+        # broadcasting / type-promoting add: the eager add, then the (relu-)fused fake-quant
+        if other is None:
+            raise RuntimeError("pre_op add needs `other`")
+        t = torch.add(x, other)
+        if pre_op == _native.PRE_ADD:
+            return _affine_scalar_cuda(t, scale, zero_point, quant_min, quant_max)
+        x, other, pre_op = t, None, _native.PRE_RELU
+    return affine_scalar_pre_direct(x, other, int(pre_op), float(np.float32(scale)), int(zero_point), int(quant_min), int(quant_max))
+
+
+# ---- prepared per-channel parameters: {1/s, s, zp} records the kernels stage with TMA bulk copies (mctq_affine_prepare)
+_AFFINE_PREPARED = {}     # (scale ptr, zp ptr, versions, C, device) -> (scale, zp kept alive so the key stays unique, blob)
+
+
+def clear_affine_caches():
+    _AFFINE_PREPARED.clear()
+
+
+def _affine_prepared(lib, scale, zero_point, index):
+    """Device blob of prepared parameters for (scale, zero_point), built once per parameter pair; None while a CUDA
+    graph is being captured and the blob does not exist yet (the raw-parameter entry point is used instead)."""
+    key = (scale.data_ptr(), zero_point.data_ptr(), scale._version, zero_point._version, scale.numel(), index)
+    ent = _AFFINE_PREPARED.get(key)
+    if ent is None:
+        if torch.cuda.is_current_stream_capturing():
+            return None
+        if len(_AFFINE_PREPARED) >= 4096:
+            _AFFINE_PREPARED.clear()
+        C = scale.numel()
+        blob = torch.empty(lib.mctq_affine_prepared_bytes(C), dtype=torch.uint8, device=scale.device)
+        stream = _raw_stream(index)
+        rc = lib.mctq_affine_prepare(scale.data_ptr(), zero_point.data_ptr(), C, blob.data_ptr(), blob.numel(), stream)
+        if rc:
+            _native.check(rc, "mctq_affine_prepare")
+        torch.cuda.current_stream(scale.device).synchronize()     # one-off: the blob may be used from any stream afterwards
+        ent = (scale, zero_point, blob)
+        _AFFINE_PREPARED[key] = ent
+    return ent[2]
+
+
+def _launch_affine_params(lib, x_ptr, y_ptr, codes_ptr, n, tag, scale, zero_point, C, inner, quant_min, quant_max, code_mode, index):
+    """mctq_fq_affine_prepared for per-channel parameters (C > 1), mctq_fq_affine otherwise.  The caller has made
+    `index` the current device."""
+    if C > 1 and scale.is_contiguous() and zero_point.is_contiguous():
+        blob = _affine_prepared(lib, scale, zero_point, index)
+        if blob is not None:
+            return lib.mctq_fq_affine_prepared(x_ptr, y_ptr, codes_ptr, n, tag, blob.data_ptr(), C, inner, 0, quant_min, quant_max,
+                                               code_mode, _raw_stream(index)), "mctq_fq_affine_prepared"
+    return lib.mctq_fq_affine(x_ptr, y_ptr, codes_ptr, n, tag, scale.data_ptr(), zero_point.data_ptr(), C, inner, 0,
+                              quant_min, quant_max, code_mode, _raw_stream(index)), "mctq_fq_affine"
+
+
 def affine_params_direct(x, scale, zero_point, C, inner, quant_min, quant_max):
     """Lean launch of mctq_fq_affine for parameter TENSORS already on x's device and already validated
     (x: plain CUDA tensor; the (C, inner) view refers to x's memory order)."""
@@ -230,12 +326,12 @@ def affine_params_direct(x, scale, zero_point, C, inner, quant_min, quant_max):
         prev = _get_device()
         if prev != index:
             _set_device(index)
-        rc = lib.mctq_fq_affine(x.data_ptr(), y.data_ptr(), None, n, tag, scale.data_ptr(), zero_point.data_ptr(), C, inner, 0,
-                                quant_min, quant_max, 0, _raw_stream(index))
+        rc, what = _launch_affine_params(lib, x.data_ptr(), y.data_ptr(), None, n, tag, scale, zero_point, C, inner,
+                                         quant_min, quant_max, 0, index)
         if prev != index:
             _set_device(prev)
         if rc:
-            _native.check(rc, "mctq_fq_affine")
+            _native.check(rc, what)
     return y
 
 
@@ -281,10 +377,10 @@ def _affine_channel_launch(x, scale, zero_point, axis, quant_min, quant_max, cod
     if n:
         lib = _native.load()
         s, z = _param_on(scale, xd.device), _param_on(zero_point, xd.device)
-        with _on_device(xd.device):
-            rc = lib.mctq_fq_affine(_ptr(xd), _ptr(y), _ptr(codes), n, tag, _ptr(s), _ptr(z), C, inner, 0,
-                                    int(quant_min), int(quant_max), int(code_mode), _stream(xd.device))
-        _native.check(rc, "mctq_fq_affine")
+        with _on_device(xd.device) as cur:
+            rc, what = _launch_affine_params(lib, _ptr(xd), _ptr(y), _ptr(codes), n, tag, s.contiguous(), z.contiguous(), C, inner,
+                                             int(quant_min), int(quant_max), int(code_mode), cur.idx)
+        _native.check(rc, what)
     return y, codes
 
 
@@ -540,6 +636,8 @@ _LIB.impl("quantize_affine_channel", _quantize_affine_channel_cuda, "CUDA")
 _LIB.impl("dequantize_affine", _dequantize_affine_cuda, "CUDA")
 _LIB.impl("lut_indices", _lut_indices_cuda, "CUDA")
 
+_LIB.impl("fq_affine_scalar_pre", _affine_scalar_pre_cuda, "CUDA")
+_LIB.impl("fq_affine_scalar_pre", _no_host_path("fq_affine_scalar_pre"), "CPU")
 _LIB.impl("fq_affine_scalar", _affine_scalar_cpu, "CPU")
 _LIB.impl("fq_affine_tensor", _affine_tensor_cpu, "CPU")
 _LIB.impl("fq_affine_channel", _affine_channel_cpu, "CPU")
@@ -553,6 +651,11 @@ _LIB.impl("lut_indices", _no_host_path("lut_indices"), "CPU")
 # --------------------------------------------------------------------------------------------- fake / meta impls
 @torch.library.register_fake("mctq::fq_affine_scalar")
 def _(x, scale, zero_point, quant_min, quant_max):
+    return torch.empty_like(x)
+
+
+@torch.library.register_fake("mctq::fq_affine_scalar_pre")
+def _(x, other, pre_op, scale, zero_point, quant_min, quant_max):
     return torch.empty_like(x)
 
 

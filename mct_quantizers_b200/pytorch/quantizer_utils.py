@@ -110,4 +110,5 @@ def lut_quantizer(tensor_data: torch.Tensor,
     # their dtype through the normalisation (the reference's eager ops round after each step)
     divisor = float(threshold) + float(eps)
     fn = ops._lut_scalar_cuda if direct else torch.ops.mctq.fq_lut_scalar
-    return fn(tensor_data, table, K, divisor, float(threshold), tensor_data.dtype in (torch.bfloat16, torch.float16))
+    # round_to_input_dtype=True is a no-op for f32 inputs; passing the constant keeps the call fx-traceable
+    return fn(tensor_data, table, K, divisor, float(threshold), True)

@@ -148,16 +148,30 @@ def _rand_x(rng, n, dtype, scale=1.0):
 SIZES = [1, 3, 4, 5, 7, 8, 9, 31, 255, 1023, 1024, 1025, 4095, 4096, 4097, 8191, 8193, 16385, 100003]
 
 
+def _affine_call(lib, prepared, xd, y, codes, n, tag, sd, zd, C, inner, elem_offset, qmin, qmax, code_mode):
+    """mctq_fq_affine, or mctq_affine_prepare + mctq_fq_affine_prepared (TMA-staged parameters) on the same arguments."""
+    if not prepared:
+        return lib.mctq_fq_affine(_vp(xd), _vp(y), _vp(codes), n, tag, _vp(sd), _vp(zd), C, inner, elem_offset, qmin, qmax,
+                                  code_mode, _stream())
+    nb = lib.mctq_affine_prepared_bytes(C)
+    blob = torch.full((nb,), 0xA5, dtype=torch.uint8, device=DEV)
+    rc = lib.mctq_affine_prepare(_vp(sd), _vp(zd), C, _vp(blob), nb, _stream())
+    assert rc == 0
+    rc = lib.mctq_fq_affine_prepared(_vp(xd), _vp(y), _vp(codes), n, tag, _vp(blob), C, inner, elem_offset, qmin, qmax,
+                                     code_mode, _stream())
+    torch.cuda.synchronize()         # blob must outlive the launch
+    return rc
+
+
+@pytest.mark.parametrize("prepared", [False, True])
 @pytest.mark.parametrize("dtype", ["float32", "bfloat16", "float16"])
 @pytest.mark.parametrize("code_mode", [0, 1, 2])
-def test_affine_ragged_sizes_and_codes(dtype, code_mode, lib):
+def test_affine_ragged_sizes_and_codes(dtype, code_mode, prepared, lib):
     """Every tail path of the tile kernel, per-tensor and per-channel, values + int8 / int4 codes vs the oracle."""
     rng = np.random.default_rng(7)
     tag = G.DT_TAG[dtype]
     for n in SIZES:
-        for (C, inner) in [(1, 1), (3, 1), (5, 7), (4, 8), (2, 4096), (7, 1000)]:
-            if C * inner > n and C > 1 and n > 16:
-                pass
+        for (C, inner) in [(1, 1), (3, 1), (5, 7), (4, 8), (2, 4096), (7, 1000), (8, 1), (12, 1), (16, 3), (300, 2)]:
             bits = 4 if code_mode == 2 else 8
             signed = (n + C) % 2 == 0
             qmin, qmax = (-(2 ** (bits - 1)), 2 ** (bits - 1) - 1) if signed else (0, 2 ** bits - 1)
@@ -169,8 +183,7 @@ def test_affine_ragged_sizes_and_codes(dtype, code_mode, lib):
             ncode = n if code_mode == 1 else (n + 1) // 2
             codes = torch.full((ncode + 8,), 0x5A, dtype=torch.uint8, device=DEV) if code_mode else None
             sd, zd = torch.from_numpy(scale).to(DEV), torch.from_numpy(zp).to(DEV)     # keep alive across the launch
-            rc = lib.mctq_fq_affine(_vp(xd), _vp(y), _vp(codes), n, tag, _vp(sd), _vp(zd), C, inner, 0, qmin, qmax,
-                                    code_mode, _stream())
+            rc = _affine_call(lib, prepared, xd, y, codes, n, tag, sd, zd, C, inner, 0, qmin, qmax, code_mode)
             assert rc == 0, (n, C, inner)
             torch.cuda.synchronize()
             want_y, want_codes = oracle.fq_affine(G.from_torch(x), tag, scale, zp, C, inner, qmin, qmax, want_codes=True)
@@ -189,8 +202,9 @@ def test_affine_ragged_sizes_and_codes(dtype, code_mode, lib):
                 assert np.array_equal(g, want_codes), (n, C, inner)
 
 
+@pytest.mark.parametrize("prepared", [False, True])
 @pytest.mark.parametrize("dtype", ["float32", "bfloat16"])
-def test_affine_elem_offset_slices(dtype, lib):
+def test_affine_elem_offset_slices(dtype, prepared, lib):
     """A tensor processed as arbitrary flat slices (elem_offset) == processed whole: the contract behind
     batch / channel-block sharding and host staging."""
     rng = np.random.default_rng(11)
@@ -207,14 +221,14 @@ def test_affine_elem_offset_slices(dtype, lib):
     for a, b in zip(cuts[:-1], cuts[1:]):
         xs = x[a:b].clone().to(DEV)          # fresh (aligned) allocation holding the slice
         ys = torch.empty_like(xs)
-        assert lib.mctq_fq_affine(_vp(xs), _vp(ys), None, b - a, tag, _vp(sd), _vp(zd), C, inner, a, 0, 255, 0, _stream()) == 0
+        assert _affine_call(lib, prepared, xs, ys, None, b - a, tag, sd, zd, C, inner, a, 0, 255, 0) == 0
         got[a:b] = G.from_torch(ys)
     assert G.bits_equal(got, want)
     # misaligned views (odd element offsets) take the scalar fallback kernel
     xd = x.to(DEV)
     for a in (1, 3, 5):
         ys = torch.empty(n - a + 1, dtype=xd.dtype, device=DEV)[1:]
-        assert lib.mctq_fq_affine(_vp(xd[a:]), _vp(ys), None, n - a, tag, _vp(sd), _vp(zd), C, inner, a, 0, 255, 0, _stream()) == 0
+        assert _affine_call(lib, prepared, xd[a:], ys, None, n - a, tag, sd, zd, C, inner, a, 0, 255, 0) == 0
         assert G.bits_equal(G.from_torch(ys), want[a:])
 
 

@@ -45,7 +45,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--mb", type=float, default=1024.0, help="input megabytes per launch")
     ap.add_argument("--reps", type=int, default=20)
-    ap.add_argument("--what", default="affine,channel,codes,lut,copy")
+    ap.add_argument("--what", default="affine,channel,fused,codes,lut,copy")
     ap.add_argument("--unroll", default="4")
     ap.add_argument("--dtypes", default="f32,bf16")
     ap.add_argument("--json", default=None)
@@ -88,13 +88,29 @@ def main():
                 report(f"affine per-tensor uniform zp u{u}", dt, 2 * n * es, med, best)
             if "channel" in what:
                 for (C, inner, label) in ((4096, 11008, "rows 11008"), (11008, 4096, "rows 4096"), (512, 4608, "conv 512x512x3x3"),
-                                          (960, 9, "depthwise inner 9"), (768, 1, "channel-last C=768"), (3, 1, "channel-last C=3")):
+                                          (960, 9, "depthwise inner 9"), (1024, 64, "rows 64"), (256, 16, "convT 4x4 inner 16"),
+                                          (768, 1, "channel-last C=768"), (3, 1, "channel-last C=3")):
                     sc = torch.rand(C, device=dev) * 0.05 + 0.01
                     zp = torch.zeros(C, dtype=torch.int32, device=dev)
                     med, best = timeit(lambda i: lib.mctq_fq_affine(vp(xs[i]), vp(ys[i]), None, n, tag, vp(sc), vp(zp), C, inner, 0, -128, 127, 0, stream()),
                                        args.reps, nbuf)
                     report(f"affine per-channel {label} u{u}", dt, 2 * n * es, med, best)
+                    if u == 4:
+                        nb = lib.mctq_affine_prepared_bytes(C)
+                        blob = torch.empty(nb, dtype=torch.uint8, device=dev)
+                        assert lib.mctq_affine_prepare(vp(sc), vp(zp), C, vp(blob), nb, stream()) == 0
+                        torch.cuda.synchronize()
+                        fn = lambda i: lib.mctq_fq_affine_prepared(vp(xs[i]), vp(ys[i]), None, n, tag, vp(blob), C, inner, 0, -128, 127, 0, stream())
+                        assert fn(0) == 0
+                        med, best = timeit(fn, args.reps, nbuf)
+                        report(f"affine-prepared per-channel {label}", dt, 2 * n * es, med, best)
         lib.mctq_set_tuning(0, 4)
+        if "fused" in what:
+            for pre, label, streams in ((1, "relu", 2), (2, "relu6", 2), (3, "add", 3), (4, "add+relu", 3)):
+                fn = lambda i: lib.mctq_fq_affine_scalar_pre(vp(xs[i]), vp(xs[(i + 1) % nbuf]), vp(ys[i]), n, tag, pre, 0.0129, 77, 0, 255, stream())
+                assert fn(0) == 0
+                med, best = timeit(fn, args.reps, nbuf)
+                report(f"fused {label} -> affine per-tensor", dt, streams * n * es, med, best)
         if "codes" in what:
             cs = [torch.empty(n, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
             med, best = timeit(lambda i: lib.mctq_fq_affine_scalar(vp(xs[i]), vp(ys[i]), vp(cs[i]), n, tag, 0.03125, 0, -128, 127, 1, stream()), args.reps, nbuf)
