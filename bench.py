@@ -65,6 +65,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=256, help="images per GPU")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profiler-range", action="store_true", help="bracket the timed region with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-batch", type=int, default=8, help="images per step of the CPU reference arm / cpu_baseline sample")
     return ap.parse_args()
@@ -80,7 +81,8 @@ class ClockSampler:
 
     def __init__(self, index, period=0.02):
         self.index, self.period = index, period
-        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.samples, self.reasons, self.max_mhz = [], set(), None       # samples: (perf_counter, MHz, reason names)
+        self.window = None
         self._stop = threading.Event()
         self._thread = None
         try:
@@ -101,14 +103,12 @@ class ClockSampler:
                  "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80)}
         while not self._stop.is_set():
             try:
-                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mhz = int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 try:
                     mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 except Exception:
                     mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for k, bit in names.items():
-                    if mask & bit:
-                        self.reasons.add(k)
+                self.samples.append((time.perf_counter(), mhz, [k for k, bit in names.items() if mask & bit]))
             except Exception:
                 pass
             self._stop.wait(self.period)
@@ -125,9 +125,17 @@ class ClockSampler:
             self._thread.join()
 
     def summary(self):
-        s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+        """Samples taken inside `window` = (t0, t1) of perf_counter (the timed region); the thread itself is started
+        before the warm-up because the first NVML queries take tens of milliseconds and stall kernel launches."""
+        lo, hi = self.window if self.window else (float("-inf"), float("inf"))
+        inside = [(m, r) for t, m, r in self.samples if lo <= t <= hi]
+        if not inside and self.samples:          # region shorter than one period: the sample closest to it
+            t, m, r = min(self.samples, key=lambda smp: min(abs(smp[0] - lo), abs(smp[0] - hi)))
+            inside = [(m, r)]
+        mhz = sorted(m for m, _ in inside)
+        reasons = sorted({k for _, r in inside for k in r})
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(mhz)}
 
 
 # ------------------------------------------------------------------------------------------------- workload
@@ -230,8 +238,10 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    import logging
     import mct_quantizers_b200 as mctq
     from mct_quantizers_b200 import _native, sharding
+    logging.getLogger("MCT Quantizers B200").setLevel(logging.ERROR)     # 53 identical "range adjusted" notices
     from mct_quantizers_b200.pytorch import quantizers as Q
     from mct_quantizers_b200.pytorch.model_quantization import WeightPlan
     lib = _native.load(build_if_missing=False)
@@ -263,16 +273,12 @@ def run_b200(args):
 
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
 
-    def step(mark=None):
+    def step():
         if wplan is not None:
             wplan.run()
-        if mark is not None:
-            mark[0].record()
         out = None
         for h, x in zip(holders, acts):
             out = h(x)
-        if mark is not None:
-            mark[1].record()
         return out
 
     def barrier():
@@ -280,25 +286,81 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    marks = [(ev(), ev()) for _ in range(args.steps)]
-    launches0 = lib.mctq_launch_count()
     sampler = ClockSampler(torch.cuda.current_device() if os.environ.get("CUDA_VISIBLE_DEVICES") is None else local_rank)
-    with sampler:
-        e0, e1 = ev(), ev()
-        barrier()
-        torch.cuda.profiler.start()         # ncu --profile-from-start off captures exactly the timed region
-        e0.record()
-        for k in range(args.steps):
-            last = step(marks[k])
-        e1.record()
-        barrier()
+    if "nosampler" in os.environ.get("MCTQ_BENCH_DEBUG", ""):
+        sampler.nv = None
+    if "nopdl" in os.environ.get("MCTQ_BENCH_DEBUG", ""):
+        lib.mctq_set_tuning(3, 0)
+    sampler.__enter__()
+    n_warm = 0
+    last = None
+    for _ in range(max(args.warmup, 3)):
+        last = step()          # same object lifetimes as the timed loop: `last` keeps one output alive across a step, and a
+        n_warm += 1            # first-time cudaMalloc by the caching allocator inside the timed region costs 3-126 ms
+    # keep warming (untimed) the way the timed region runs -- back-to-back steps, no host sync in between -- for ~0.5 s:
+    # clocks settle under the power cap and every allocator / driver first-time cost is paid here
+    torch.cuda.synchronize()
+    t_settle = time.perf_counter()
+    prev_ev = None
+    while time.perf_counter() - t_settle < 0.5:
+        for _ in range(10):
+            last = step()
+            n_warm += 1
+        ev_s = ev()
+        ev_s.record()
+        if prev_ev is not None:
+            prev_ev.synchronize()            # bound the launch queue without draining it: wait for the batch BEFORE this one
+        prev_ev = ev_s
+    barrier()
+    # duration of the weights launch alone (one multi-tensor kernel, ~1 % of a step), measured here so that no event has
+    # to be recorded in the middle of a timed step
+    w_ms = 0.0
+    if wplan is not None:
+        wa, wb = ev(), ev()
+        reps_w = 20
+        wplan.run()
+        wa.record()
+        for _ in range(reps_w):
+            wplan.run()
+        wb.record()
+        wb.synchronize()
+        w_ms = wa.elapsed_time(wb) / reps_w
+    launches0 = lib.mctq_launch_count()
+    e0, e1 = ev(), ev()
+    step_ev = [ev() for _ in range(args.steps + 1)]
+    # torch creates the underlying cudaEvent lazily at the first record(): create them all before the timed region
+    for e in [e0, e1] + step_ev:
+        e.record()
+    import gc
+    gc.collect()
+    gc.disable()                         # no interpreter-heap collection inside the timed loop
+    barrier()
+    if args.profiler_range:              # ncu --profile-from-start off captures exactly the timed region
+        torch.cuda.profiler.start()
+    t_region0 = time.perf_counter()
+    e0.record()
+    step_ev[0].record()
+    dbg = os.environ.get("MCTQ_BENCH_DEBUG", "")
+    cpu_t = [time.perf_counter()]
+    for k in range(args.steps):
+        last = step()
+        if "nostepev" not in dbg:
+            step_ev[k + 1].record()
+        cpu_t.append(time.perf_counter())
+    e1.record()
+    barrier()
+    gc.enable()
+    sampler.window = (t_region0, time.perf_counter())
+    if args.profiler_range:
         torch.cuda.profiler.stop()
+    sampler.__exit__()
     launches = lib.mctq_launch_count() - launches0
     ms_total = e0.elapsed_time(e1)
-    act_ms = sum(a.elapsed_time(b) for a, b in marks)
+    if "nostepev" in dbg:
+        per_step = [ms_total / args.steps]
+    else:
+        per_step = [step_ev[k].elapsed_time(step_ev[k + 1]) for k in range(args.steps)]
+    act_ms = ms_total - w_ms * args.steps        # the 53 activation launches of every step
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     tot_bytes = torch.tensor([float(bytes_step)], device=dev, dtype=torch.float64)
     if world > 1:
@@ -371,8 +433,24 @@ def run_b200(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         achieved = n_a * BYTES_PER_ELEM / (act_ms / args.steps * 1e-3) / 1e9
+        # dram bytes per launch of the dominant kernel: from the committed ncu capture of this same command
+        # (profiles/r01_bench_traffic.json, made by tools/ncu_summary.py traffic); only valid for the default batch
+        traffic, traffic_src = None, None
+        try:
+            if args.batch == 256:
+                with open(os.path.join(ROOT, "profiles", "r01_bench_traffic.json")) as f:
+                    for k, v in json.load(f).items():
+                        if k.startswith("fq_affine_kernel<float, 0, 0, 4"):
+                            traffic = int(v["dram_bytes_per_launch"])
+                            traffic_src = "profiles/r01_bench_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the 53 launches of a step)"
+        except Exception:
+            pass
         line = {"metric": METRIC, "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
+                "warmup": max(args.warmup, 3), "warmup_steps_run": n_warm, "ms_per_step": round(ms_step, 4),
+                "step_ms": {"min": round(min(per_step), 4), "median": round(sorted(per_step)[len(per_step) // 2], 4),
+                            "max": round(max(per_step), 4), "first": [round(v, 4) for v in per_step[:3]],
+                            "cpu_launch_ms_first": [round((b - a) * 1e3, 3) for a, b in zip(cpu_t[:6], cpu_t[1:7])],
+                            "cpu_launch_ms_max": round(max(b - a for a, b in zip(cpu_t, cpu_t[1:])) * 1e3, 3)}, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "batch_per_gpu": args.batch, "elements_per_step_per_gpu": n_w + n_a,
                            "bytes_per_element": BYTES_PER_ELEM, "l2": "inputs larger than L2 (6.8 GB read + 6.8 GB written per step)",
@@ -380,9 +458,11 @@ def run_b200(args):
                 "elements_per_s": round(value * 1e9 / BYTES_PER_ELEM, 1),
                 "pct_of_8TBs": round(100 * value / world / 8000.0, 2),
                 "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                             "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                             "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                              "kernel": "fq_affine_kernel<float, CH_PT, no codes, unroll 4> (ActivationUniform sites)",
+                             "launches_per_step": len(acts),
                              "avg_launch_us": round(act_ms / args.steps / len(acts) * 1e3, 2),
+                             "how": "CUDA events around every timed step minus the weights launch (%.1f us, timed separately)" % (w_ms * 1e3),
                              "algorithmic_bytes_per_launch": int(n_a * BYTES_PER_ELEM / len(acts))},
                 "clocks": clocks, "gpu_launches": int(launches), "checksums": checks}
         if e2e is not None:

@@ -469,8 +469,11 @@ template <typename T, int CHMODE, int CODE, bool RINT>
 int launch_affine_unroll(const AffineArgs& a, cudaStream_t st) {
     // the unroll sweep (mctq_set_tuning key 0) exists only for the plain fake-quant variants
     if (CODE == MCTQ_CODES_NONE && !RINT) {
-        if (g_unroll == 2) return launch_affine_tiles<T, CHMODE, MCTQ_CODES_NONE, 2, false>(a, st);
-        if (g_unroll == 8) return launch_affine_tiles<T, CHMODE, MCTQ_CODES_NONE, 8, false>(a, st);
+        // automatic: 8 KB tiles for per-tensor launches (nothing to stage per tile; tools/stream_probe.cu measures
+        // +2 % over 16 KB tiles), 16 KB tiles when a channel window is staged per tile
+        const int u = g_unroll ? g_unroll : (CHMODE == CH_PT ? 2 : 4);
+        if (u == 2) return launch_affine_tiles<T, CHMODE, MCTQ_CODES_NONE, 2, false>(a, st);
+        if (u == 8) return launch_affine_tiles<T, CHMODE, MCTQ_CODES_NONE, 8, false>(a, st);
     }
     return launch_affine_tiles<T, CHMODE, CODE, 4, RINT>(a, st);
 }
@@ -514,7 +517,7 @@ int launch_affine_typed(const AffineArgs& a, int code_mode, cudaStream_t st) {
             if (period <= 4096) { chmode = CH_LAST; a2.period = (uint32_t)period; }
         }
     }
-    if (a.prep_rec && !rint_path && g_unroll == 4) {
+    if (a.prep_rec && !rint_path && (g_unroll == 0 || g_unroll == 4)) {
         // prepared blob: bulk-copy staging needs 16-byte granules (CH_LAST: whole arrays of C floats)
         if (chmode == CH_VEC) return launch_affine_prepared<T, CH_VEC>(a2, code_mode, st);
         if (chmode == CH_ELEM) return launch_affine_prepared<T, CH_ELEM>(a2, code_mode, st);

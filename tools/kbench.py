@@ -46,7 +46,7 @@ def main():
     ap.add_argument("--mb", type=float, default=1024.0, help="input megabytes per launch")
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--what", default="affine,channel,fused,codes,lut,copy")
-    ap.add_argument("--unroll", default="4")
+    ap.add_argument("--unroll", default="0", help="0 = the library default (automatic)")
     ap.add_argument("--dtypes", default="f32,bf16")
     ap.add_argument("--json", default=None)
     args = ap.parse_args()
@@ -95,7 +95,7 @@ def main():
                     med, best = timeit(lambda i: lib.mctq_fq_affine(vp(xs[i]), vp(ys[i]), None, n, tag, vp(sc), vp(zp), C, inner, 0, -128, 127, 0, stream()),
                                        args.reps, nbuf)
                     report(f"affine per-channel {label} u{u}", dt, 2 * n * es, med, best)
-                    if u == 4:
+                    if u in (0, 4):
                         nb = lib.mctq_affine_prepared_bytes(C)
                         blob = torch.empty(nb, dtype=torch.uint8, device=dev)
                         assert lib.mctq_affine_prepare(vp(sc), vp(zp), C, vp(blob), nb, stream()) == 0
@@ -104,7 +104,7 @@ def main():
                         assert fn(0) == 0
                         med, best = timeit(fn, args.reps, nbuf)
                         report(f"affine-prepared per-channel {label}", dt, 2 * n * es, med, best)
-        lib.mctq_set_tuning(0, 4)
+        lib.mctq_set_tuning(0, 0)
         if "fused" in what:
             for pre, label, streams in ((1, "relu", 2), (2, "relu6", 2), (3, "add", 3), (4, "add+relu", 3)):
                 fn = lambda i: lib.mctq_fq_affine_scalar_pre(vp(xs[i]), vp(xs[(i + 1) % nbuf]), vp(ys[i]), n, tag, pre, 0.0129, 77, 0, 255, stream())
@@ -128,7 +128,7 @@ def main():
             table = lut_search_table(lut, 8, True).to(dev)
             for x in xs:
                 x.normal_(0, 0.02)
-            for u in [int(v) for v in args.unroll.split(",") if int(v) in (4, 8)] or [4]:
+            for u in [int(v) for v in args.unroll.split(",") if int(v) in (0, 4, 8)] or [0]:
                 lib.mctq_set_tuning(0, u)
                 for (C, inner, label) in ((4096, 11008, "rows 11008"), (11008, 4096, "rows 4096"), (1, 1, "per-tensor")):
                     thr = torch.rand(C, device=dev) * 0.05 + 0.06
@@ -138,7 +138,7 @@ def main():
                 med, best = timeit(lambda i: lib.mctq_fq_lut_scalar(vp(xs[i]), vp(yf[i]), None, n, tag, vp(table), 16, 0.125, 0.125, int(es == 2), 0, stream()),
                                    args.reps, nbuf)
                 report(f"lut K=16 activation scalar u{u}", dt, n * (es + 4), med, best)
-            lib.mctq_set_tuning(0, 4)
+            lib.mctq_set_tuning(0, 0)
             # prepared path: per-channel decision tables in the x domain (built once, outside the timed region)
             table_host = lut_search_table(lut, 8, True)
             for (C, inner, label) in ((4096, 11008, "rows 11008"), (11008, 4096, "rows 4096"), (1, 1, "per-tensor"), (65536, 64, "rows 64")):

@@ -48,3 +48,25 @@ for elems in (n, 64 << 20, 16 << 20, 4 << 20, 1 << 20):
     x = h_in[:elems]
     dt = t(lambda: q(x), reps=5)
     print(f"host-staged fake-quant of {elems * 4 / 1e6:8.1f} MB: {dt * 1e3:8.3f} ms  {2 * elems * 4 / dt / 1e9:6.1f} GB/s algorithmic")
+
+# zero-copy: the streaming kernel reads / writes PINNED host memory directly over PCIe (UVA), no staging, no chunk pipeline
+import ctypes  # noqa: E402
+from mct_quantizers_b200 import _native  # noqa: E402
+lib = _native.load()
+st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)  # noqa: E731
+h_y = torch.empty(n, dtype=torch.float32, pin_memory=True)
+for elems in (n, 64 << 20, 16 << 20, 4 << 20, 1 << 20, 1 << 18):
+    def zc():
+        rc = lib.mctq_fq_affine_scalar(h_in.data_ptr(), h_y.data_ptr(), None, elems, 0, 0.0215, 116, 0, 255, 0, st())
+        assert rc == 0
+        torch.cuda.current_stream().synchronize()
+    dt = t(zc, reps=5)
+    print(f"zero-copy fake-quant of {elems * 4 / 1e6:8.1f} MB: {dt * 1e3:8.3f} ms  {2 * elems * 4 / dt / 1e9:6.1f} GB/s algorithmic")
+for u in (2, 8):
+    lib.mctq_set_tuning(0, u)
+    def zc():
+        lib.mctq_fq_affine_scalar(h_in.data_ptr(), h_y.data_ptr(), None, n, 0, 0.0215, 116, 0, 255, 0, st())
+        torch.cuda.current_stream().synchronize()
+    dt = t(zc, reps=3)
+    print(f"zero-copy 1 GiB unroll {u}: {2 * n * 4 / dt / 1e9:6.1f} GB/s algorithmic")
+lib.mctq_set_tuning(0, 0)
