@@ -420,7 +420,9 @@ def run_b200(args):
                "d2h_bytes_per_step": n_e2e * 4, "steps": args.e2e_steps, "ms_per_step": round(td.item() * 1e3, 3),
                "batch_per_gpu": e2e_batch,
                "path": "quantizer(cpu_pinned_tensor) -> mctq_fq_affine_host: chunked H2D / kernel / D2H on 3 streams"}
-        assert sharding.checksum64(res[: min(8, res.shape[0])]) == sharding.checksum64(last[: min(8, res.shape[0])]) or world >= 1
+        # the host-buffer path must give the device path's bits (same inputs: host_acts are copies of acts)
+        if sharding.checksum64(res) != sharding.checksum64(last[:e2e_batch]):
+            raise RuntimeError("e2e (host-buffer) result differs from the device-resident result")
         del host_acts, host_w
 
     if rank == 0:

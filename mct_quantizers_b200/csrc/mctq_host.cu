@@ -7,6 +7,7 @@ int g_unroll = 0;           // 0 = automatic (per-tensor tiles: 2 vectors per th
 int g_force_rint = 0;
 int g_force_ieee_div = 0;
 int g_pdl = 1;
+int g_lut_shfl = 1;
 }  // namespace mctq
 
 using namespace mctq;
@@ -28,6 +29,7 @@ int mctq_set_tuning(int key, int value) {
         case 1: prev = g_force_rint; g_force_rint = value ? 1 : 0; return prev;
         case 2: prev = g_force_ieee_div; g_force_ieee_div = value ? 1 : 0; return prev;
         case 3: prev = g_pdl; g_pdl = value ? 1 : 0; return prev;
+        case 4: prev = g_lut_shfl; g_lut_shfl = value ? 1 : 0; return prev;
         default: return MCTQ_E_BADARG;
     }
 }

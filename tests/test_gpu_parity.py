@@ -254,8 +254,10 @@ def test_lut_ragged_sizes(dtype, lib):
             assert G.bits_equal(y.cpu().numpy(), want), (n, C, inner, G.mismatch_report(y.cpu().numpy(), want))
 
 
-def test_lut_all_table_sizes_and_ieee_variant(lib):
-    """K = 1 .. 256 centroids (every padded search depth), fast division vs the IEEE-division variant."""
+@pytest.mark.parametrize("shuffle_search", [1, 0])
+def test_lut_all_table_sizes_and_ieee_variant(shuffle_search, lib):
+    """K = 1 .. 256 centroids (every padded search depth), fast division vs the IEEE-division variant, warp-shuffle
+    search (tables of <= 32 entries) vs the shared-memory search."""
     from mct_quantizers_b200.pytorch.quantizer_utils import lut_search_table
     rng = np.random.default_rng(9)
     n = 50000
@@ -269,11 +271,13 @@ def test_lut_all_table_sizes_and_ieee_variant(lib):
         want, want_idx = oracle.fq_lut(x.numpy(), oracle.F32, lut, thr, 3, 5, 8, True, 1e-8, want_idx=True)
         for ieee in (0, 1):
             lib.mctq_set_tuning(2, ieee)
+            lib.mctq_set_tuning(4, shuffle_search)
             y = torch.empty(n, dtype=torch.float32, device=DEV)
             idx = torch.empty(n, dtype=torch.uint8, device=DEV)
             rc = lib.mctq_fq_lut(_vp(xd), _vp(y), _vp(idx) if not ieee else None, n, 0, _vp(table), K,
                                  _vp(td), 3, 5, 0, float(np.float32(1e-8)), 0 if ieee else 1, _stream())
             lib.mctq_set_tuning(2, 0)
+            lib.mctq_set_tuning(4, 1)
             assert rc == 0
             assert G.bits_equal(y.cpu().numpy(), want), (K, ieee)
             if not ieee:

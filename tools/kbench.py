@@ -154,6 +154,12 @@ def main():
                     assert fn(0) == 0
                     med, best = timeit(fn, args.reps, nbuf)
                     report(f"lut-prepared K=16 weights {label}{lab}", dt, n * (es + 4 + (0.5 if mode else 0)), med, best)
+            lib.mctq_set_tuning(4, 0)
+            thr = torch.rand(4096, device=dev) * 0.05 + 0.06
+            med, best = timeit(lambda i: lib.mctq_fq_lut(vp(xs[i]), vp(yf[i]), None, n, tag, vp(table), 16, vp(thr), 4096, 11008, 0, 1e-8, 0, stream()),
+                               args.reps, nbuf)
+            report("lut K=16 weights rows 11008 shared-memory search (no shuffles)", dt, n * (es + 4), med, best)
+            lib.mctq_set_tuning(4, 1)
             lib.mctq_set_tuning(2, 1)
             thr = torch.rand(4096, device=dev) * 0.05 + 0.06
             med, best = timeit(lambda i: lib.mctq_fq_lut(vp(xs[i]), vp(yf[i]), None, n, tag, vp(table), 16, vp(thr), 4096, 11008, 0, 1e-8, 0, stream()),
