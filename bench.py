@@ -416,8 +416,8 @@ def run_b200(args):
         if world > 1:
             dist.all_reduce(td, op=dist.ReduceOp.MAX)
             dist.all_reduce(nb, op=dist.ReduceOp.SUM)
-        e2e = {"value": round(nb.item() / td.item() / 1e9, 3), "unit": "GB/s", "h2d_bytes_per_step": n_e2e * 4,
-               "d2h_bytes_per_step": n_e2e * 4, "steps": args.e2e_steps, "ms_per_step": round(td.item() * 1e3, 3),
+        e2e = {"value": round(nb.item() / td.item() / 1e9, 3), "unit": "GB/s", "h2d_bytes_per_step": int(nb.item()) // 2,
+               "d2h_bytes_per_step": int(nb.item()) // 2, "steps": args.e2e_steps, "ms_per_step": round(td.item() * 1e3, 3),
                "batch_per_gpu": e2e_batch,
                "path": "quantizer(cpu_pinned_tensor) -> mctq_fq_affine_host: chunked H2D / kernel / D2H on 3 streams"}
         # the host-buffer path must give the device path's bits (same inputs: host_acts are copies of acts)

@@ -361,16 +361,75 @@ __global__ void __launch_bounds__(kThreads) dequant_affine_kernel(const void* co
 // ------------------------------------------------------------------------------------------ multi-tensor
 constexpr int kMultiTile = 2048;   // elements per tile, any dtype
 
-template <typename T>
+// channel of logical element i: 32-bit arithmetic whenever the tensor has fewer than 2^32 elements
+__device__ __forceinline__ int64_t multi_channel(int64_t i, const MctqTensorDesc& d, bool small) {
+    if (d.C <= 1) return 0;
+    if (small) return (int64_t)(((uint32_t)i / (uint32_t)d.inner) % (uint32_t)d.C);
+    return (i / d.inner) % d.C;
+}
+
+template <typename T, bool RINT>
 __device__ __forceinline__ void multi_tile_body(const MctqTensorDesc& d, int64_t e0) {
+    using Op = AffineOp<RINT>;
+    constexpr int V = 4;                                   // elements per vector: 16 B (f32) or 8 B (bf16 / f16)
+    constexpr int WORDS = V * sizeof(T) / 4;
+    constexpr int NV = kMultiTile / (kThreads * V);        // vectors per thread (2)
     const T* x = reinterpret_cast<const T*>(d.x);
     T* y = reinterpret_cast<T*>(d.y);
-    const int64_t e1 = min(e0 + (int64_t)kMultiTile, d.n);
-    const bool fast = (d.qmax - d.qmin) < kFastRangeLimit;
+    const int64_t rem = d.n - e0;
+    const bool small = d.n < (1LL << 32) && d.inner < (1LL << 32) && d.C < (1LL << 32);
     AffineArgs a;
     a.qmin = d.qmin;
     a.qmax = d.qmax;
-    // 8 elements per thread, strided by the CTA width so that every access is coalesced
+    const bool vec = (d.C <= 1 || d.inner % V == 0) && (reinterpret_cast<uintptr_t>(x) % (V * sizeof(T))) == 0 &&
+                     (!y || (reinterpret_cast<uintptr_t>(y) % (V * sizeof(T))) == 0) &&
+                     (!d.codes || d.code_mode != MCTQ_CODES_INT8 || (reinterpret_cast<uintptr_t>(d.codes) & 3u) == 0);
+    if (vec) {
+        // one channel per aligned vector of 4: load both vectors and their parameters first, then one reciprocal per vector
+        uint32_t w[NV][WORDS];
+        float sc[NV];
+        int zp[NV];
+        bool whole[NV];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int64_t l = (int64_t)(j * kThreads + threadIdx.x) * V;
+            whole[j] = l + V <= rem;
+            if (whole[j]) ld_words<WORDS>(x + e0 + l, w[j]);
+            else {
+                T tmp[V];
+#pragma unroll
+                for (int e = 0; e < V; ++e) tmp[e] = (l + e < rem) ? x[e0 + l + e] : from_f32<T>(0.0f);
+                memcpy(w[j], tmp, sizeof(tmp));
+            }
+            const int64_t c = l < rem ? multi_channel(e0 + l, d, small) : 0;
+            sc[j] = __ldg(d.scale + c);
+            zp[j] = __ldg(d.zp + c);
+        }
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int64_t l = (int64_t)(j * kThreads + threadIdx.x) * V;
+            if (l >= rem) continue;
+            const typename Op::ChanParams p = Op::make(sc[j], zp[j], a);
+            float f[V];
+            int code[V];
+            Pack<T, V>::unpack(w[j], f);
+#pragma unroll
+            for (int e = 0; e < V; ++e) f[e] = Op::template apply<true>(f[e], p, code[e]);
+            if (whole[j]) {
+                if (y) { Pack<T, V>::pack(f, w[j]); st_words<WORDS>(y + e0 + l, w[j]); }
+                if (d.codes && d.code_mode == MCTQ_CODES_INT8) st_codes<V, MCTQ_CODES_INT8>(d.codes, e0 + l, code);
+            } else {
+                for (int e = 0; e < V && l + e < rem; ++e) {
+                    if (y) y[e0 + l + e] = from_f32<T>(f[e]);
+                    if (d.codes && d.code_mode == MCTQ_CODES_INT8) reinterpret_cast<uint8_t*>(d.codes)[e0 + l + e] = (uint8_t)(code[e] & 0xff);
+                }
+            }
+        }
+        return;
+    }
+    // rows that are not a multiple of 4 (depthwise 3x3, first conv ...) or misaligned views: 8 elements per thread,
+    // strided by the CTA width so that every access is coalesced; one channel look-up per element
+    const int64_t e1 = min(e0 + (int64_t)kMultiTile, d.n);
     float xv[kMultiTile / kThreads];
 #pragma unroll
     for (int k = 0; k < kMultiTile / kThreads; ++k) {
@@ -381,13 +440,9 @@ __device__ __forceinline__ void multi_tile_body(const MctqTensorDesc& d, int64_t
     for (int k = 0; k < kMultiTile / kThreads; ++k) {
         int64_t i = e0 + k * kThreads + threadIdx.x;
         if (i < e1) {
-            int64_t c = d.C > 1 ? (i / d.inner) % d.C : 0;
-            float s = __ldg(d.scale + c);
-            int zp = __ldg(d.zp + c);
+            const int64_t c = multi_channel(i, d, small);
             int code;
-            float out;
-            if (fast) out = AffineOp<false>::apply<true>(xv[k], AffineOp<false>::make(s, zp, a), code);
-            else out = AffineOp<true>::apply<true>(xv[k], AffineOp<true>::make(s, zp, a), code);
+            const float out = Op::template apply<true>(xv[k], Op::make(__ldg(d.scale + c), __ldg(d.zp + c), a), code);
             if (y) y[i] = from_f32<T>(out);
             if (d.codes && d.code_mode == MCTQ_CODES_INT8) reinterpret_cast<uint8_t*>(d.codes)[i] = (uint8_t)(code & 0xff);
         }
@@ -407,9 +462,10 @@ __global__ void __launch_bounds__(kThreads) fq_affine_multi_kernel(const MctqTen
     }
     const MctqTensorDesc d = descs[lo];
     const int64_t e0 = (int64_t)(tile - __ldg(tile_starts + lo)) * kMultiTile;
-    if (d.dtype == MCTQ_F32) multi_tile_body<float>(d, e0);
-    else if (d.dtype == MCTQ_BF16) multi_tile_body<__nv_bfloat16>(d, e0);
-    else multi_tile_body<__half>(d, e0);
+    const bool fast = (int64_t)d.qmax - d.qmin < kFastRangeLimit;
+    if (d.dtype == MCTQ_F32) { if (fast) multi_tile_body<float, false>(d, e0); else multi_tile_body<float, true>(d, e0); }
+    else if (d.dtype == MCTQ_BF16) { if (fast) multi_tile_body<__nv_bfloat16, false>(d, e0); else multi_tile_body<__nv_bfloat16, true>(d, e0); }
+    else { if (fast) multi_tile_body<__half, false>(d, e0); else multi_tile_body<__half, true>(d, e0); }
 }
 
 }  // namespace mctq

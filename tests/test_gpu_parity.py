@@ -501,3 +501,50 @@ def test_whole_model_single_launch(Q, lib):
         assert torch.equal(per_layer['weight'], fused[name]['weight'])
     for mod in model.children():
         assert mod.quantize_weights_batched().keys() == {'weight'}
+
+
+@pytest.mark.parametrize("dtype", ["float32", "bfloat16", "float16"])
+def test_multi_tensor_kernel_vs_oracle(dtype, lib):
+    """mctq_fq_affine_multi over a mixed descriptor table: rows that are / are not multiples of 4, ragged tails,
+    per-tensor entries, int8 codes, a misaligned view -- every tensor bit-equal to the oracle."""
+    import ctypes
+    from mct_quantizers_b200 import _native
+    rng = np.random.default_rng(21)
+    tag = G.DT_TAG[dtype]
+    specs = [(1, 1, 5), (1, 1, 4099), (16, 27, 16 * 27), (32, 9, 32 * 9), (8, 64, 8 * 64 * 3), (5, 4, 5 * 4 * 103),
+             (64, 576, 64 * 576), (3, 2048, 3 * 2048 + 0), (7, 12, 7 * 12 * 11), (1, 1, 2048), (6, 1, 6 * 500)]
+    keep, descs, wants = [], (_native.MctqTensorDesc * len(specs))(), []
+    for k, (C, inner, n) in enumerate(specs):
+        signed = k % 2 == 0
+        qmin, qmax = (-128, 127) if signed else (0, 255)
+        scale = (np.abs(rng.standard_normal(C)) * 0.03 + 0.004).astype(np.float32)
+        zp = np.zeros(C, np.int32) if signed else rng.integers(0, 256, size=C).astype(np.int32)
+        x = _rand_x(rng, n, dtype, 1.0)
+        off = 1 if k == 5 else 0                                   # one misaligned view
+        xd_full = torch.empty(n + off, dtype=x.dtype, device=DEV)
+        xd = xd_full[off:]
+        xd.copy_(x)
+        y = torch.empty(n + off, dtype=x.dtype, device=DEV)[off:]
+        codes = torch.full((n + 8,), 0x5A, dtype=torch.uint8, device=DEV) if k % 3 == 0 else None
+        sd, zd = torch.from_numpy(scale).to(DEV), torch.from_numpy(zp).to(DEV)
+        keep += [xd_full, xd, y, codes, sd, zd]
+        d = descs[k]
+        d.x, d.y, d.codes, d.scale, d.zp = xd.data_ptr(), y.data_ptr(), codes.data_ptr() if codes is not None else None, sd.data_ptr(), zd.data_ptr()
+        d.n, d.C, d.inner, d.qmin, d.qmax, d.dtype, d.code_mode = n, C, inner, qmin, qmax, tag, 1 if codes is not None else 0
+        want_y, want_codes = oracle.fq_affine(G.from_torch(x), tag, scale, zp, C, inner, qmin, qmax, want_codes=True)
+        wants.append((y, codes, want_y, want_codes, signed, n))
+    starts = (ctypes.c_int32 * (len(specs) + 1))()
+    total = lib.mctq_multi_plan(ctypes.cast(descs, ctypes.c_void_p), len(specs), ctypes.cast(starts, ctypes.c_void_p))
+    assert total > 0
+    descs_dev = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8).to(DEV)
+    starts_dev = torch.frombuffer(bytearray(bytes(starts)), dtype=torch.uint8).to(DEV)
+    assert lib.mctq_fq_affine_multi(_vp(descs_dev), _vp(starts_dev), len(specs), total, _stream()) == 0
+    torch.cuda.synchronize()
+    for k, (y, codes, want_y, want_codes, signed, n) in enumerate(wants):
+        got = G.from_torch(y)
+        assert G.bits_equal(got, want_y), (k, specs[k], G.mismatch_report(got, want_y))
+        if codes is not None:
+            c = codes.cpu().numpy()
+            assert (c[n:] == 0x5A).all()
+            g = c[:n].view(np.int8).astype(np.int32) if signed else c[:n].astype(np.int32)
+            assert np.array_equal(g, want_codes), (k, specs[k])
