@@ -48,10 +48,13 @@ static int prep_geometry(int K, int bw, int is_signed, int64_t C, PrepGeom* g) {
     while (nc < need) nc <<= 1;
     if (nc > 4096) return MCTQ_E_RANGE;           // table would not fit comfortably in shared memory
     g->NC = (int)nc;
-    g->rec_floats = 2 * g->P + 4;
+    // everything the hot kernel stages with 16-byte bulk copies (cells | orig, channel records) starts on a 16-byte
+    // boundary and is a multiple of 16 bytes long, also for tables of one or two entries
+    g->rec_floats = (2 * g->P + 4 + 3) & ~3;
     size_t o = sizeof(LutPrepHeader);
     g->off_tau = o; o += (size_t)g->P * 4;
     g->off_cq = o; o += (size_t)g->P * 4;
+    o = (o + 15) & ~(size_t)15;
     g->off_cells = o; o += ((size_t)g->NC + 1 + 15) & ~(size_t)15;
     g->off_orig = o; o += ((size_t)g->P + 15) & ~(size_t)15;
     g->off_rec = o; o += (size_t)C * g->rec_floats * 4;
