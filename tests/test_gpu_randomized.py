@@ -39,6 +39,12 @@ def _tensor(rng, shape, dtype, scale):
     return x
 
 
+def _host_variants(x):
+    """The same values as HOST tensors: pageable (staged through the GPU in chunks) and pinned (small pinned tensors are
+    read / written by the kernel directly over PCIe)."""
+    return [x.clone(), x.clone().pin_memory()]
+
+
 def _layouts(x, rng):
     """x itself, a permuted-but-dense view, and a strided (non-dense) view holding the same values."""
     out = [x]
@@ -73,6 +79,9 @@ def test_weights_symmetric_and_pot(seed, Q):
         for xl in _layouts(x, rng):
             got = q(xl.to(DEV))
             assert _same(got, want), (shape, dtype, bits, per_channel, axis, pot, xl.stride())
+        for xh in _host_variants(x):
+            got = q(xh)
+            assert not got.is_cuda and _same(got, want), ("host", shape, dtype, bits, per_channel, axis, pot)
 
 
 @pytest.mark.parametrize("seed", range(12))
@@ -95,6 +104,9 @@ def test_weights_uniform(seed, Q):
         for xl in _layouts(x, rng):
             got = q(xl.to(DEV))
             assert _same(got, want), (shape, dtype, bits, per_channel, axis, xl.stride())
+        for xh in _host_variants(x):
+            got = q(xh)
+            assert not got.is_cuda and _same(got, want), ("host", shape, dtype, bits, per_channel, axis)
 
 
 @pytest.mark.parametrize("seed", range(8))
@@ -120,6 +132,9 @@ def test_activation_affine(seed, Q):
         want = port.affine_scalar_qparams(x, scale, zp, qmin, qmax)
         for xl in _layouts(x, rng):
             assert _same(q(xl.to(DEV)), want), (shape, dtype, bits, kind, xl.stride())
+        for xh in _host_variants(x):
+            got = q(xh)
+            assert not got.is_cuda and _same(got, want), ("host", shape, dtype, bits, kind)
 
 
 @pytest.mark.parametrize("seed", range(8))
@@ -145,6 +160,9 @@ def test_lut_weights(seed, Q):
         for xl in _layouts(x, rng):
             got = q(xl.to(DEV))
             assert _same(got, want), (shape, dtype, bits, K, per_channel, axis, pot, xl.stride())
+        for xh in _host_variants(x):
+            got = q(xh)
+            assert not got.is_cuda and _same(got, want), ("host", shape, dtype, bits, K, per_channel, axis, pot)
 
 
 @pytest.mark.parametrize("seed", range(6))
@@ -165,3 +183,60 @@ def test_lut_activations(seed, Q):
         for xl in _layouts(x, rng):
             got = q(xl.to(DEV))
             assert _same(got, want), (shape, dtype, bits, K, signed, thr, xl.stride())
+        for xh in _host_variants(x):
+            got = q(xh)
+            assert not got.is_cuda and _same(got, want), ("host", shape, dtype, bits, K, signed, thr)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_integer_codes_and_lut_indices(seed, Q):
+    """Code / index emission through the torch.library operators against the C oracle: int8 and packed int4."""
+    import oracle
+    import mct_quantizers_b200  # noqa: F401  (registers torch.ops.mctq)
+    from mct_quantizers_b200.pytorch.quantizer_utils import lut_search_table
+    rng = np.random.default_rng(6000 + seed)
+    tags = {torch.float32: oracle.F32, torch.bfloat16: oracle.BF16, torch.float16: oracle.F16}
+    for _ in range(5):
+        shape = _shape(rng)
+        dtype = DTYPES[int(rng.integers(0, 3))]
+        axis = int(rng.integers(0, len(shape)))
+        C = shape[axis]
+        inner = int(np.prod(shape[axis + 1:]))
+        x = _tensor(rng, shape, dtype, 1.5)
+        xb = x.numpy() if dtype == torch.float32 else x.view(torch.int16).numpy().view(np.uint16)
+        n = x.numel()
+        for bits in (8, 4):
+            signed = bool(rng.integers(0, 2))
+            qmin, qmax = (-(2 ** (bits - 1)), 2 ** (bits - 1) - 1) if signed else (0, 2 ** bits - 1)
+            scale = (np.abs(rng.standard_normal(C)) * 0.05 + 0.01).astype(np.float32)
+            zp = np.zeros(C, np.int32) if signed else rng.integers(qmin, qmax + 1, size=C).astype(np.int32)
+            mode = 1 if bits == 8 else 2
+            codes, y = torch.ops.mctq.quantize_affine_channel(x.to(DEV), torch.from_numpy(scale).to(DEV), torch.from_numpy(zp).to(DEV),
+                                                               axis, qmin, qmax, mode, True)
+            want_y, want_codes = oracle.fq_affine(xb.reshape(-1), tags[dtype], scale, zp, C, inner, qmin, qmax, want_codes=True)
+            got_y = y.cpu().reshape(-1)
+            got_y = got_y.numpy() if dtype == torch.float32 else got_y.view(torch.int16).numpy().view(np.uint16)
+            assert np.array_equal(got_y.view(want_y.dtype), want_y)
+            c = codes.cpu().numpy().reshape(-1)
+            if mode == 1:
+                g = c.view(np.int8).astype(np.int32) if signed else c.view(np.uint8).astype(np.int32)
+            else:
+                nib = np.stack([c & 0xF, c >> 4], 1).reshape(-1)[:n].astype(np.int32)
+                g = np.where(nib >= 8, nib - 16, nib) if signed else nib
+            assert np.array_equal(g, want_codes), (shape, dtype, axis, bits, signed)
+            # dequantising the codes gives the fake-quantised values (f32)
+            yd = torch.ops.mctq.dequantize_affine(codes, mode, signed, list(shape), torch.from_numpy(scale).to(DEV),
+                                                  torch.from_numpy(zp).to(DEV), axis)
+            ref = ((want_codes - zp[(np.arange(n) // inner) % C]).astype(np.float32) * scale[(np.arange(n) // inner) % C]).astype(np.float32)
+            assert np.array_equal(yd.cpu().numpy().reshape(-1).view(np.uint32), ref.view(np.uint32))
+        # LUT indices
+        K = int(rng.integers(1, 17))
+        lut = rng.choice(np.arange(-128, 128), size=K, replace=False).astype(np.float32)
+        thr = rng.uniform(0.05, 3.0, size=C).astype(np.float32)
+        table = lut_search_table(lut, 8, True)
+        for mode in (1, 2):
+            idx = torch.ops.mctq.lut_indices(x.to(DEV), table, K, torch.from_numpy(thr).to(DEV), True, axis, 1e-8, mode)
+            _, want_idx = oracle.fq_lut(xb.reshape(-1), tags[dtype], lut, thr, C, inner, 8, True, 1e-8, want_idx=True)
+            c = idx.cpu().numpy().reshape(-1)
+            g = c.astype(np.int32) if mode == 1 else np.stack([c & 0xF, c >> 4], 1).reshape(-1)[:n].astype(np.int32)
+            assert np.array_equal(g[:n], want_idx), (shape, dtype, axis, K, mode)
