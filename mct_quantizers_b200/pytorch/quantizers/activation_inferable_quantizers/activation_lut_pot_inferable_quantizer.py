@@ -34,7 +34,7 @@ class ActivationLutPOTInferableQuantizer(BaseLUTSymmetricInferableQuantizer):
         self._search_table = None
 
     def __call__(self, inputs: torch.Tensor):
-        if self._search_table is None:
+        if self.__dict__.get('_search_table') is None:     # also absent in objects unpickled from the reference
             self._search_table = lut_search_table(self._lut_values_np, self.lut_values_bitwidth, self.signed)
         # the table stays on the host: the operator keeps per-device copies and the prepared per-channel decision
         # tables (nothing here touches inputs.device, so the call is fx-traceable)

@@ -25,7 +25,7 @@ def lut_weights_call(q, inputs, export_fn):
         outputs = export_fn()
     else:
         inputs.requires_grad = False
-        if q._search_table is None:            # built lazily: needs the native library, which loads on first use
+        if q.__dict__.get('_search_table') is None:   # built lazily (native library loads on first use; absent in objects unpickled from the reference)
             q._search_table = lut_search_table(q._lut_values_np, q.lut_values_bitwidth, True)
         thr, = q._on(inputs.device, q._threshold_torch)
         outputs = lut_quantizer(inputs, lut_values=q._lut_values_torch, signed=True, threshold=thr,
