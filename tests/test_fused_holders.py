@@ -168,3 +168,21 @@ def test_cuda_graph_capture_of_a_quantized_block(fuse):
             g.replay()
             want = model(xn)
             assert torch.equal(static_y.view(torch.int32), want.view(torch.int32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("backend", ["eager", "aot_eager"])
+def test_torch_compile_sees_the_custom_ops(backend):
+    """torch.compile (dynamo capture + fake-tensor propagation through the registered fake kernels) of a model with
+    wrappers, holders and fused holders gives the eager result; the ops stay opaque calls into the CUDA library."""
+    dev = torch.device("cuda:0")
+    torch.manual_seed(2)
+    model = Block().to(dev).eval()
+    fused = mctq.fuse_activation_producers(model)
+    x = torch.randn(4, 4, 17, 19, device=dev)
+    with torch.no_grad():
+        want = model(x)
+        for m in (model, fused):
+            compiled = torch.compile(m, backend=backend)
+            got = compiled(x)
+            assert torch.equal(got.view(torch.int32), want.view(torch.int32))
