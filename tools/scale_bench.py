@@ -149,7 +149,35 @@ def main():
             del xs
             torch.cuda.empty_cache()
 
-    # verification outside the timed regions: checksums of one small output, gathered with NCCL
+    # verification outside the timed regions (the only NCCL traffic of the tool): every rank fake-quantizes ITS shard of
+    # a tensor all ranks can regenerate (same seed), the shards are all-gathered over NVLink and compared bit for bit
+    # with the unsharded result -- batch sharding (activations) and channel-block sharding (per-channel weights)
+    gv = torch.Generator(device=dev).manual_seed(4321)
+    full = torch.empty((64 * world, 197, 768), device=dev).normal_(0, 1, generator=gv).bfloat16()
+    qa = Q.ActivationSymmetricInferableQuantizer(8, [3.7], True)
+    r0, r1 = sharding.shard_batch(full.shape[0], world, rank)
+    mine_out = qa(full[r0:r1].contiguous())
+    Wf = torch.empty((64 * world, 1024), device=dev).normal_(0, 0.02, generator=gv)
+    thr_all = Wf.abs().amax(1).double().cpu().tolist()
+    slices, (c0, c1) = sharding.shard_channel_blocks(Wf.shape, 0, world, rank)
+    qw_shard = Q.WeightsSymmetricInferableQuantizer(8, thr_all[c0:c1], True, 0)
+    w_out = qw_shard(Wf[slices].contiguous())
+    if world > 1:
+        gathered = torch.empty_like(full)
+        dist.all_gather_into_tensor(gathered, mine_out)
+        wg = torch.empty_like(Wf)
+        dist.all_gather_into_tensor(wg, w_out)
+    else:
+        gathered, wg = mine_out, w_out
+    ok_a = torch.equal(gathered.view(torch.int16), qa(full).view(torch.int16))
+    ok_w = torch.equal(wg.view(torch.int32), Q.WeightsSymmetricInferableQuantizer(8, thr_all, True, 0)(Wf).view(torch.int32))
+    assert ok_a and ok_w, ("sharded result differs from the unsharded one", ok_a, ok_w)
+    if rank == 0:
+        print(f"verification: all-gathered batch shards ({tuple(full.shape)} bf16) and channel-block shards ({tuple(Wf.shape)} f32) "
+              f"== unsharded results, N={world}", flush=True)
+    rows.append({"config": "verification all-gather (batch shards + channel-block shards) == unsharded", "n_gpus": world, "ok": True})
+
+    # checksums of one small output, gathered with NCCL
     y = qs[0][1](torch.arange(4096, device=dev, dtype=torch.float32) * 0.01 - 20.0)
     chk = torch.tensor([sharding.checksum64(y)], device=dev, dtype=torch.int64)
     if world > 1:
