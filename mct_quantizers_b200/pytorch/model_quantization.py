@@ -71,3 +71,63 @@ def quantize_model_weights(model: torch.nn.Module) -> Dict[str, Dict[str, torch.
     for owner, name, y in zip(owners, plan.names, plan.run()):
         result.setdefault(owner, {})[name] = y
     return result
+
+
+class ModelWeightPlan:
+    """Whole-model weight quantization hoisted out of the per-layer forward.
+
+    The reference re-quantizes every wrapped weight inside every `PytorchQuantizationWrapper.forward`
+    (mct_quantizers/pytorch/quantize_wrapper.py:228-240).  A plan gathers the weights of ALL wrappers of a model,
+    quantizes them with one multi-tensor launch (`refresh()`), installs the results in the wrapped layers and tells the
+    wrappers to skip their own quantization while the plan is active:
+
+        plan = plan_model_weights(model)      # builds the descriptor table once, output buffers are reused
+        with plan:                            # refresh(): ONE kernel for every affine weight quantizer of the model
+            y = model(x)                      # wrappers run their layers on the installed weights, no per-layer launches
+
+    or, for inference with constant weights, `plan.enable()` once (and `plan.refresh()` again only if the float weights
+    change).  Results are identical to the per-layer path (same kernels' arithmetic, checked by tests)."""
+
+    def __init__(self, model: torch.nn.Module):
+        from mct_quantizers_b200.pytorch.quantize_wrapper import PytorchQuantizationWrapper
+        self.wrappers, triples, self._owner = [], [], []
+        for mod in model.modules():
+            if isinstance(mod, PytorchQuantizationWrapper) and mod.is_weights_quantization:
+                self.wrappers.append(mod)
+                for name, w, q in mod.get_weights_vars():
+                    triples.append((name, w, q))
+                    self._owner.append(mod)
+        self.plan = WeightPlan(triples) if triples else None
+        self.active = False
+
+    def refresh(self):
+        """Quantize every weight (one launch for the affine quantizers) and install the results."""
+        if self.plan is None:
+            return
+        per_wrapper = {}
+        for owner, name, y in zip(self._owner, self.plan.names, self.plan.run()):
+            per_wrapper.setdefault(id(owner), (owner, {}))[1][name] = y
+        for owner, weights in per_wrapper.values():
+            owner.set_quantize_weights(weights)
+
+    def enable(self):
+        self.refresh()
+        for w in self.wrappers:
+            w._prequantized = True
+        self.active = True
+        return self
+
+    def disable(self):
+        for w in self.wrappers:
+            w._prequantized = False
+        self.active = False
+
+    def __enter__(self):
+        return self.enable()
+
+    def __exit__(self, *exc):
+        self.disable()
+
+
+def plan_model_weights(model: torch.nn.Module) -> ModelWeightPlan:
+    return ModelWeightPlan(model)

@@ -130,7 +130,8 @@ class PytorchQuantizationWrapper(nn.Module):
         return flags
 
     def forward(self, *args: List[Any], **kwargs: Dict[str, Any]) -> Union[torch.Tensor, List[torch.Tensor]]:
-        if self.is_weights_quantization:
+        # (a ModelWeightPlan that is active has already installed this forward's quantized weights: model_quantization.py)
+        if self.is_weights_quantization and not self.__dict__.get('_prequantized', False):
             quantized_weights = {}
             for (name, unquantized_weight, quantizer), wants_training in zip(self._weights_vars, self._training_flags()):
                 if wants_training:

@@ -548,3 +548,47 @@ def test_multi_tensor_kernel_vs_oracle(dtype, lib):
             assert (c[n:] == 0x5A).all()
             g = c[:n].view(np.int8).astype(np.int32) if signed else c[:n].astype(np.int32)
             assert np.array_equal(g, want_codes), (k, specs[k])
+
+
+def test_model_weight_plan_hoists_weight_quantization(Q, lib):
+    """plan_model_weights: one launch for all wrappers, forwards inside the plan launch nothing of ours for weights and
+    give the per-layer path's result bit for bit; positional (constant) weights are covered too."""
+    import mct_quantizers_b200 as mctq
+    torch.manual_seed(3)
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            convs = [torch.nn.Conv2d(3, 8, 3, padding=1), torch.nn.Conv2d(8, 8, 3, padding=1, groups=8), torch.nn.Conv2d(8, 4, 1)]
+            self.layers = torch.nn.ModuleList()
+            for c in convs:
+                thr = [float(v) for v in c.weight.detach().abs().flatten(1).amax(1)]
+                self.layers.append(mctq.PytorchQuantizationWrapper(c, {'weight': Q.WeightsSymmetricInferableQuantizer(8, thr, True, 0)}))
+            const = torch.randn(4, 1, 1)
+            self.sub = mctq.PytorchQuantizationWrapper(torch.sub, {1: Q.WeightsUniformInferableQuantizer(8, [-2.0], [2.0], False)}, {1: const})
+
+        def forward(self, x):
+            for layer in self.layers:
+                x = layer(x)
+            return self.sub(x)
+
+    model = Net().to(DEV).eval()
+    x = torch.randn(2, 3, 16, 16, device=DEV)
+    with torch.no_grad():
+        want = model(x)
+        c0 = lib.mctq_launch_count()
+        model(x)
+        per_layer_launches = lib.mctq_launch_count() - c0
+        assert per_layer_launches == 4
+        plan = mctq.plan_model_weights(model)
+        c0 = lib.mctq_launch_count()
+        with plan:
+            assert lib.mctq_launch_count() - c0 == 1            # refresh(): one multi-tensor launch
+            got = model(x)
+            got2 = model(x)
+            assert lib.mctq_launch_count() - c0 == 1            # the forwards launched no weight kernels
+        assert torch.equal(got.view(torch.int32), want.view(torch.int32)) and torch.equal(got2.view(torch.int32), want.view(torch.int32))
+        c0 = lib.mctq_launch_count()
+        again = model(x)                                        # plan left: per-layer path is back
+        assert lib.mctq_launch_count() - c0 == per_layer_launches
+        assert torch.equal(again.view(torch.int32), want.view(torch.int32))
