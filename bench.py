@@ -287,10 +287,6 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     sampler = ClockSampler(torch.cuda.current_device() if os.environ.get("CUDA_VISIBLE_DEVICES") is None else local_rank)
-    if "nosampler" in os.environ.get("MCTQ_BENCH_DEBUG", ""):
-        sampler.nv = None
-    if "nopdl" in os.environ.get("MCTQ_BENCH_DEBUG", ""):
-        lib.mctq_set_tuning(3, 0)
     sampler.__enter__()
     n_warm = 0
     last = None
@@ -340,12 +336,10 @@ def run_b200(args):
     t_region0 = time.perf_counter()
     e0.record()
     step_ev[0].record()
-    dbg = os.environ.get("MCTQ_BENCH_DEBUG", "")
     cpu_t = [time.perf_counter()]
     for k in range(args.steps):
         last = step()
-        if "nostepev" not in dbg:
-            step_ev[k + 1].record()
+        step_ev[k + 1].record()
         cpu_t.append(time.perf_counter())
     e1.record()
     barrier()
@@ -356,10 +350,7 @@ def run_b200(args):
     sampler.__exit__()
     launches = lib.mctq_launch_count() - launches0
     ms_total = e0.elapsed_time(e1)
-    if "nostepev" in dbg:
-        per_step = [ms_total / args.steps]
-    else:
-        per_step = [step_ev[k].elapsed_time(step_ev[k + 1]) for k in range(args.steps)]
+    per_step = [step_ev[k].elapsed_time(step_ev[k + 1]) for k in range(args.steps)]
     act_ms = ms_total - w_ms * args.steps        # the 53 activation launches of every step
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     tot_bytes = torch.tensor([float(bytes_step)], device=dev, dtype=torch.float64)

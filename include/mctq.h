@@ -112,8 +112,9 @@ int mctq_fq_affine_prepared(const void* x, void* y, void* codes, int64_t n, int 
 int mctq_fq_affine_scalar_pre(const void* x, const void* x2, void* y, int64_t n, int x_dtype, int pre_op, float scale,
                               int32_t zp, int32_t qmin, int32_t qmax, void* stream);
 
-/* Dequantise codes written by the functions above: y = (q - zp) * s  (f32 out).  No reference call site:
- * this is the consumer side of the code wire format. */
+/* Dequantise codes written by the functions above: y = (q - zp) * s  (f32 out; exact for |q - zp| < 2^22, i.e. for any
+ * zero point inside the code range).  No reference call site: this is the consumer side of the code wire format
+ * (SURVEY 8f rank 2). */
 int mctq_dequant_affine(const void* codes, int code_mode, int is_signed, float* y, int64_t n,
                         const float* scale, const int32_t* zp, int64_t C, int64_t inner, int64_t elem_offset,
                         void* stream);

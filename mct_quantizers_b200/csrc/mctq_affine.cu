@@ -358,6 +358,92 @@ __global__ void __launch_bounds__(kThreads) dequant_affine_kernel(const void* co
     }
 }
 
+// Streaming consumer of the code wire format: tile = 256 threads x 4 vectors x 4 elements; a vector is 4 codes (one 32-bit
+// load for int8, 16 bits for packed int4) and one 16-byte f32 store.  5 (int8) / 4.5 (int4) algorithmic bytes per element.
+//   MODE 0  per-tensor: parameters loaded once per thread
+//   MODE 1  per-channel, rows a multiple of 4: one channel (one division, two parameter loads) per vector
+//   MODE 2  per-channel, any row length below 2^32: the vector's first channel from one 32-bit division, the following
+//           elements walk (rem, c) forward
+// (q - zp) -> float goes through the magic-number trick (integer add into the mantissa of 1.5 * 2^23, one FADD) instead of
+// a quarter-rate I2F: exact for |q - zp| < 2^22.
+template <int CODE, int MODE>
+__global__ void __launch_bounds__(kThreads) dequant_affine_vec_kernel(const void* codes, int is_signed, float* y, int64_t n,
+                                                                      const float* __restrict__ scale, const int32_t* __restrict__ zp,
+                                                                      uint32_t C, uint32_t inner, int64_t elem_offset,
+                                                                      const FastDiv div_inner, const FastDiv div_C) {
+    constexpr int V = 4, UNROLL = 4;
+    constexpr int64_t TILE = (int64_t)kThreads * UNROLL * V;
+    const int64_t t0 = (int64_t)blockIdx.x * TILE;
+    pdl_wait();
+    pdl_launch_dependents();
+    uint32_t raw[UNROLL];
+#pragma unroll
+    for (int j = 0; j < UNROLL; ++j) {
+        const int64_t e = t0 + (int64_t)(j * kThreads + threadIdx.x) * V;
+        raw[j] = 0;
+        if (e + V <= n) {
+            if (CODE == MCTQ_CODES_INT8) raw[j] = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(codes) + e));
+            else raw[j] = __ldg(reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(codes) + (e >> 1)));
+        } else {
+            for (int k = 0; k < V && e + k < n; ++k) {
+                const int64_t i = e + k;
+                if (CODE == MCTQ_CODES_INT8) raw[j] |= (uint32_t)reinterpret_cast<const uint8_t*>(codes)[i] << (8 * k);
+                else raw[j] |= (uint32_t)((reinterpret_cast<const uint8_t*>(codes)[i >> 1] >> ((i & 1) * 4)) & 0xf) << (4 * k);
+            }
+        }
+    }
+    float s0 = 0.0f;
+    int z0 = 0;
+    if (MODE == 0) { s0 = __ldg(scale); z0 = __ldg(zp); }
+    const bool small = (uint64_t)(elem_offset + n) < (1ull << 31);
+#pragma unroll
+    for (int j = 0; j < UNROLL; ++j) {
+        const int64_t e = t0 + (int64_t)(j * kThreads + threadIdx.x) * V;
+        if (e >= n) continue;
+        uint32_t c = 0, rem = 0;
+        float sv = s0;
+        int zv = z0;
+        if (MODE != 0) {
+            const uint64_t g = (uint64_t)(elem_offset + e);
+            if (small) {                                        // the usual case (< 2^31 elements): multiply-shift division
+                const uint32_t g32 = (uint32_t)g, r = fdiv_u32(g32, div_inner);
+                rem = g32 - r * inner;
+                c = r - fdiv_u32(r, div_C) * C;
+            } else {
+                const uint64_t r = g / inner;
+                rem = (uint32_t)(g - r * inner);
+                c = (uint32_t)(r % C);
+            }
+            sv = __ldg(scale + c);
+            zv = __ldg(zp + c);
+        }
+        float out[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            int q;
+            if (CODE == MCTQ_CODES_INT8) {
+                q = is_signed ? (int)(int8_t)(raw[j] >> (8 * k)) : (int)((raw[j] >> (8 * k)) & 0xffu);
+            } else {
+                const int nib = (int)((raw[j] >> (4 * k)) & 0xfu);
+                q = is_signed ? ((nib ^ 8) - 8) : nib;
+            }
+            const float d = __fsub_rn(__int_as_float(0x4B400000 + (q - zv)), kMagic);        // (float)(q - zp), exact
+            out[k] = __fmul_rn(d, sv);
+            if (MODE == 2) {
+                if (++rem == inner) {
+                    rem = 0;
+                    c = (c + 1 == C) ? 0 : c + 1;
+                    sv = __ldg(scale + c);
+                    zv = __ldg(zp + c);
+                }
+            }
+        }
+        if (e + V <= n) st_stream(reinterpret_cast<uint4*>(y + e), make_uint4(__float_as_uint(out[0]), __float_as_uint(out[1]),
+                                                                               __float_as_uint(out[2]), __float_as_uint(out[3])));
+        else for (int k = 0; k < V && e + k < n; ++k) y[e + k] = out[k];
+    }
+}
+
 // ------------------------------------------------------------------------------------------ multi-tensor
 constexpr int kMultiTile = 2048;   // elements per tile, any dtype
 
@@ -664,9 +750,22 @@ int mctq_dequant_affine(const void* codes, int code_mode, int is_signed, float* 
                         const int32_t* zp, int64_t C, int64_t inner, int64_t elem_offset, void* stream) {
     if (!codes || !y || !scale || !zp || n < 0 || C < 1 || inner < 1) return MCTQ_E_BADARG;
     if (n == 0) return 0;
+    if (code_mode != MCTQ_CODES_INT8 && code_mode != MCTQ_CODES_INT4) return MCTQ_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (aligned16(y) && (reinterpret_cast<uintptr_t>(codes) & 3u) == 0 && C < (1LL << 32) && inner < (1LL << 32)) {
+        const int64_t tile = (int64_t)kThreads * 16;
+        const int64_t tiles = (n + tile - 1) / tile;
+        if (tiles > 0x7fffffffLL) return MCTQ_E_BADARG;
+        const int mode = C == 1 ? 0 : ((inner % 4 == 0 && elem_offset % 4 == 0) ? 1 : 2);
+        const uint32_t C32 = (uint32_t)C, in32 = (uint32_t)(C == 1 ? 1 : inner);
+        const FastDiv di = make_fastdiv(in32), dc = make_fastdiv(C32);
+#define MCTQ_DQ(CM, MD) launch_streaming(dequant_affine_vec_kernel<CM, MD>, (unsigned)tiles, 0, st, codes, is_signed, y, n, scale, zp, C32, in32, elem_offset, di, dc)
+        if (code_mode == MCTQ_CODES_INT8) return mode == 0 ? MCTQ_DQ(MCTQ_CODES_INT8, 0) : mode == 1 ? MCTQ_DQ(MCTQ_CODES_INT8, 1) : MCTQ_DQ(MCTQ_CODES_INT8, 2);
+        return mode == 0 ? MCTQ_DQ(MCTQ_CODES_INT4, 0) : mode == 1 ? MCTQ_DQ(MCTQ_CODES_INT4, 1) : MCTQ_DQ(MCTQ_CODES_INT4, 2);
+#undef MCTQ_DQ
+    }
     int64_t blocks = (n + kThreads - 1) / kThreads;
     if (blocks > 148 * 32) blocks = 148 * 32;
-    cudaStream_t st = (cudaStream_t)stream;
     if (code_mode == MCTQ_CODES_INT8)
         dequant_affine_kernel<MCTQ_CODES_INT8><<<(unsigned)blocks, kThreads, 0, st>>>(codes, is_signed, y, n, scale, zp, C, inner, elem_offset);
     else if (code_mode == MCTQ_CODES_INT4)

@@ -119,7 +119,17 @@ def main():
             report("affine per-tensor int8 codes only", dt, n * (es + 1), med, best)
             med, best = timeit(lambda i: lib.mctq_fq_affine_scalar(vp(xs[i]), vp(ys[i]), vp(cs[i]), n, tag, 0.5, 0, -8, 7, 2, stream()), args.reps, nbuf)
             report("affine per-tensor + int4 codes", dt, n * (2 * es + 0.5), med, best)
-            del cs
+            # consumer side of the code wire format: codes -> f32 values (5 / 4.5 algorithmic bytes per element)
+            yf32 = [torch.empty(n, dtype=torch.float32, device=dev) for _ in range(nbuf)]
+            for (C, inner, label) in ((1, 1, "per-tensor"), (4096, n // 4096 // 8 * 8 or 8, "per-channel long rows"), (960, 9, "per-channel inner 9")):
+                sc = torch.rand(C, device=dev) * 0.05 + 0.01
+                zp = torch.zeros(C, dtype=torch.int32, device=dev)
+                for mode, cb, lab in ((1, 1.0, "int8"), (2, 0.5, "int4")):
+                    fn = lambda i: lib.mctq_dequant_affine(vp(cs[i]), mode, 1, vp(yf32[i]), n, vp(sc), vp(zp), C, inner, 0, stream())
+                    assert fn(0) == 0
+                    med, best = timeit(fn, args.reps, nbuf)
+                    report(f"dequant {lab} codes -> f32 {label}", dt, n * (cb + 4), med, best)
+            del cs, yf32
         if "lut" in what:
             del ys
             yf = [torch.empty(n, dtype=torch.float32, device=dev) for _ in range(nbuf)]
