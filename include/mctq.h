@@ -206,14 +206,22 @@ int mctq_fq_lut_prepared(const void* x, float* y, void* idx, int64_t n, int x_dt
  * Host-buffer entry points: the same operators for tensors that live in HOST memory (pinned memory
  * overlaps; pageable memory works but serialises).  The data is streamed through `staging_dev`
  * (device scratch owned by the caller, >= mctq_host_staging_min_bytes()) in chunks on internal streams:
- * H2D copy, kernel and D2H copy of neighbouring chunks overlap.  Parameters are HOST arrays.  These
- * calls return after y_host is complete (they synchronise their internal streams only).
+ * H2D copy, kernel and D2H copy of neighbouring chunks overlap.  Parameters are HOST arrays (copied
+ * before the call returns; at most 384 Ki channels).  By default these calls return after y_host is
+ * complete (they synchronise their internal streams only).
  * They are what a CPU-tensor call of a quantizer maps to: the product has no CPU arithmetic path.
+ *
+ * Deferred mode (mctq_host_set_deferred(device, 1)): the calls return as soon as their copies and kernels
+ * are enqueued, so the three-stage pipeline keeps running across the tensors of a model instead of
+ * filling and draining once per tensor; x_host must stay valid and y_host is complete only after
+ * mctq_host_wait(device) (or after deferred mode is switched off, which waits as well).
  */
 size_t mctq_host_staging_min_bytes(void);
 int mctq_fq_affine_host(const void* x_host, void* y_host, int64_t n, int x_dtype,
                         const float* scale_host, const int32_t* zp_host, int64_t C, int64_t inner,
                         int32_t qmin, int32_t qmax, void* staging_dev, size_t staging_bytes, int device);
+int mctq_host_set_deferred(int device, int on);
+int mctq_host_wait(int device);
 int mctq_fq_lut_host(const void* x_host, float* y_host, int64_t n, int x_dtype,
                      const void* table_host, int K, const float* thr_host, int64_t C, int64_t inner,
                      float eps, int scalar_mode, float divisor, float thr_f32, int round_to_x_dtype,

@@ -19,3 +19,4 @@ from mct_quantizers_b200.pytorch.model_quantization import quantize_model_weight
 from mct_quantizers_b200.pytorch import quantizers as pytorch_quantizers
 from mct_quantizers_b200.pytorch.fused_activation_holder import PytorchFusedActivationQuantizationHolder, \
     fuse_activation_producers
+from mct_quantizers_b200.ops import host_pipeline

@@ -51,6 +51,8 @@ SIGNATURES = {
     "mctq_lut_prepare": (c_int, [c_vp, c_int, c_vp, c_i64, c_f32, c_int, c_f32, c_f32, c_int, c_vp, c_sz, c_vp]),
     "mctq_fq_lut_prepared": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_int, c_int, c_i64, c_i64, c_i64, c_int, c_vp]),
     "mctq_host_staging_min_bytes": (c_sz, []),
+    "mctq_host_set_deferred": (c_int, [c_int, c_int]),
+    "mctq_host_wait": (c_int, [c_int]),
     "mctq_fq_affine_host": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_vp, c_sz, c_int]),
     "mctq_fq_lut_host": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_i64, c_i64, c_f32, c_int, c_f32, c_f32,
                                  c_int, c_vp, c_sz, c_int]),

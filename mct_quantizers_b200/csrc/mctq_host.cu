@@ -40,10 +40,25 @@ int mctq_set_tuning(int key, int value) {
 namespace {
 constexpr int kHostStreams = 3;
 constexpr size_t kHostChunkBytesIn = 32u << 20;      // largest input chunk (slot size); small tensors use smaller chunks
+constexpr size_t kParamAreaBytes = 16u << 20;        // head of the staging buffer: parameters (device side)
+// The parameter area is a ring of kRing entries so that the uploads of call i + 1 never overwrite what the kernels of
+// call i are still reading (calls overlap in deferred mode).  Entry layout: [scale | thr : 1.5 MB][zp : 1.5 MB][LUT table : 1 MB].
+constexpr int kRing = 4;
+constexpr size_t kRingEntryBytes = kParamAreaBytes / kRing;
+constexpr size_t kRingArrayBytes = 1536u << 10;
+constexpr size_t kRingTableBytes = 1u << 20;
+
 struct HostCtx {
     int device = -1;
     cudaStream_t st[kHostStreams] = {nullptr, nullptr, nullptr};
+    cudaStream_t st_par = nullptr;                   // parameter uploads: never queued behind a data chunk
     cudaEvent_t params_ready = nullptr;
+    int deferred = 0;                                // calls return without synchronising (mctq_host_set_deferred)
+    uint64_t next_chunk = 0;                         // round-robin position over the streams / slots, continues across calls
+    uint64_t ring_pos = 0;
+    uint8_t* pin = nullptr;                          // pinned host mirror of the parameter ring
+    cudaEvent_t uploaded[kRing] = {};                // the H2D copy out of pin entry e has finished
+    cudaEvent_t released[kRing][kHostStreams] = {};  // the last kernel of stream i that reads device entry e has finished
 };
 HostCtx g_hctx[16];
 
@@ -57,14 +72,35 @@ int host_ctx(int device, HostCtx** out) {
             e = cudaStreamCreateWithFlags(&c.st[i], cudaStreamNonBlocking);
             if (e != cudaSuccess) return (int)e;
         }
+        e = cudaStreamCreateWithFlags(&c.st_par, cudaStreamNonBlocking);
+        if (e != cudaSuccess) return (int)e;
         e = cudaEventCreateWithFlags(&c.params_ready, cudaEventDisableTiming);
         if (e != cudaSuccess) return (int)e;
+        e = cudaHostAlloc(reinterpret_cast<void**>(&c.pin), kParamAreaBytes, cudaHostAllocDefault);
+        if (e != cudaSuccess) return (int)e;
+        for (int r = 0; r < kRing; ++r) {
+            e = cudaEventCreateWithFlags(&c.uploaded[r], cudaEventDisableTiming);
+            if (e != cudaSuccess) return (int)e;
+            for (int i = 0; i < kHostStreams; ++i) {
+                e = cudaEventCreateWithFlags(&c.released[r][i], cudaEventDisableTiming);
+                if (e != cudaSuccess) return (int)e;
+            }
+        }
         c.device = device;
     }
     *out = &c;
     return 0;
 }
 size_t dtype_size(int dt) { return dt == MCTQ_F32 ? 4 : 2; }
+
+int sync_all(HostCtx* ctx) {
+    cudaError_t e = cudaStreamSynchronize(ctx->st_par);
+    for (int i = 0; i < kHostStreams; ++i) {
+        cudaError_t e2 = cudaStreamSynchronize(ctx->st[i]);
+        if (e == cudaSuccess) e = e2;
+    }
+    return cuda_rc(e);
+}
 
 // chunk length: about an eighth of the tensor so that uploads, kernels and downloads of neighbouring chunks overlap
 // even for tensors of a few tens of MB, between 1 MB of input and the slot size, a multiple of 64 Ki elements
@@ -93,49 +129,109 @@ bool zero_copy_ok(const void* x_host, const void* y_host, int64_t n, size_t in_e
     return (size_t)n * in_es <= kZeroCopyMaxBytesIn && is_pinned(x_host) && is_pinned(y_host);
 }
 
-// H2D -> launch(chunk) -> D2H for every chunk, round-robin over the internal streams; returns when y_host is complete.
-// `launch(d_in, d_out, count, elem_offset, stream)` enqueues the kernel for one chunk.  `params_on_stream0`: the caller
-// has enqueued parameter uploads on stream 0 that the other streams must wait for.
-template <class Launch>
-int run_pipeline(HostCtx* ctx, uint8_t* slots, const uint8_t* x_host, uint8_t* y_host, int64_t n, size_t in_es, size_t out_es,
-                 bool params_on_stream0, Launch launch) {
-    cudaError_t e = cudaSuccess;
-    int rc = 0;
-    const int64_t chunk_elems = pick_chunk_elems(n, in_es, in_es > out_es ? in_es : out_es);
-    const int64_t n_chunks = (n + chunk_elems - 1) / chunk_elems;
-    const int used = (int)(n_chunks < kHostStreams ? n_chunks : kHostStreams);
-    if (params_on_stream0 && used > 1) {
-        cudaEventRecord(ctx->params_ready, ctx->st[0]);
-        for (int i = 1; i < used; ++i) cudaStreamWaitEvent(ctx->st[i], ctx->params_ready, 0);
+// One host-buffer call.  Parameters (if any) go through ring entry `e` of the pinned mirror and the device parameter
+// area on the dedicated parameter stream; the data goes H2D -> launch(chunk) -> D2H chunk by chunk, round-robin over the
+// data streams, continuing where the previous call stopped.  In the default mode the call returns when y_host is
+// complete; in deferred mode it returns as soon as everything is enqueued (mctq_host_wait completes the results), so
+// that the pipeline never drains between the tensors of a model.
+struct HostCall {
+    HostCtx* ctx;
+    uint8_t* base;           // staging buffer
+    int entry = -1;          // ring entry holding this call's parameters (-1: none)
+    uint8_t* d_entry = nullptr;
+    uint8_t* h_entry = nullptr;
+
+    // reserve a ring entry; returns its pinned host address to be filled before upload()
+    int begin_params() {
+        entry = (int)(ctx->ring_pos++ % kRing);
+        d_entry = base + (size_t)entry * kRingEntryBytes;
+        h_entry = ctx->pin + (size_t)entry * kRingEntryBytes;
+        return cuda_rc(cudaEventSynchronize(ctx->uploaded[entry]));     // host side: the previous upload out of h_entry is done
     }
-    int k = 0;
-    for (int64_t off = 0; off < n; off += chunk_elems, ++k) {
-        const int64_t cnt = (n - off) < chunk_elems ? (n - off) : chunk_elems;
-        cudaStream_t st = ctx->st[k % kHostStreams];
-        uint8_t* d_in = slots + (size_t)(k % kHostStreams) * 3 * kHostChunkBytesIn;
-        uint8_t* d_out = d_in + kHostChunkBytesIn;
-        e = cudaMemcpyAsync(d_in, x_host + off * in_es, cnt * in_es, cudaMemcpyHostToDevice, st);
-        if (e != cudaSuccess) break;
-        rc = launch(d_in, d_out, cnt, off, st);
-        if (rc) break;
-        e = cudaMemcpyAsync(y_host + off * out_es, d_out, cnt * out_es, cudaMemcpyDeviceToHost, st);
-        if (e != cudaSuccess) break;
+    int upload(size_t off, size_t bytes) {
+        return cuda_rc(cudaMemcpyAsync(d_entry + off, h_entry + off, bytes, cudaMemcpyHostToDevice, ctx->st_par));
     }
-    for (int i = 0; i < kHostStreams; ++i) {
-        if (i >= used && !(i == 0 && params_on_stream0)) continue;
-        cudaError_t e2 = cudaStreamSynchronize(ctx->st[i]);
-        if (e == cudaSuccess && e2 != cudaSuccess) e = e2;
+    int before_uploads() {
+        // device side: every kernel that read the previous contents of this entry has finished
+        for (int i = 0; i < kHostStreams; ++i) {
+            cudaError_t e = cudaStreamWaitEvent(ctx->st_par, ctx->released[entry][i], 0);
+            if (e != cudaSuccess) return (int)e;
+        }
+        return 0;
     }
-    if (rc) return rc;
-    return cuda_rc(e);
-}
+    int after_uploads() {
+        cudaError_t e = cudaEventRecord(ctx->uploaded[entry], ctx->st_par);
+        if (e != cudaSuccess) return (int)e;
+        return cuda_rc(cudaEventRecord(ctx->params_ready, ctx->st_par));
+    }
+
+    template <class Launch>
+    int run(const uint8_t* x_host, uint8_t* y_host, int64_t n, size_t in_es, size_t out_es, bool zero_copy, Launch launch) {
+        cudaError_t e = cudaSuccess;
+        int rc = 0;
+        bool used[kHostStreams] = {false, false, false};
+        auto stream_for = [&](uint64_t k) {
+            const int i = (int)(k % kHostStreams);
+            if (!used[i]) {
+                used[i] = true;
+                if (entry >= 0) cudaStreamWaitEvent(ctx->st[i], ctx->params_ready, 0);
+            }
+            return i;
+        };
+        if (zero_copy) {
+            // the kernel reads x_host / writes y_host over PCIe through their unified virtual addresses
+            const int i = stream_for(ctx->next_chunk++);
+            rc = launch(x_host, y_host, n, 0, ctx->st[i]);
+        } else {
+            uint8_t* slots = base + kParamAreaBytes;
+            const int64_t chunk_elems = pick_chunk_elems(n, in_es, in_es > out_es ? in_es : out_es);
+            for (int64_t off = 0; off < n; off += chunk_elems) {
+                const int64_t cnt = (n - off) < chunk_elems ? (n - off) : chunk_elems;
+                const int i = stream_for(ctx->next_chunk++);
+                cudaStream_t st = ctx->st[i];
+                uint8_t* d_in = slots + (size_t)i * 3 * kHostChunkBytesIn;
+                uint8_t* d_out = d_in + kHostChunkBytesIn;
+                e = cudaMemcpyAsync(d_in, x_host + off * in_es, cnt * in_es, cudaMemcpyHostToDevice, st);
+                if (e != cudaSuccess) break;
+                rc = launch(d_in, d_out, cnt, off, st);
+                if (rc) break;
+                e = cudaMemcpyAsync(y_host + off * out_es, d_out, cnt * out_es, cudaMemcpyDeviceToHost, st);
+                if (e != cudaSuccess) break;
+            }
+        }
+        if (entry >= 0)
+            for (int i = 0; i < kHostStreams; ++i)
+                if (used[i]) cudaEventRecord(ctx->released[entry][i], ctx->st[i]);
+        if (!ctx->deferred || rc || e != cudaSuccess) {
+            const int rs = sync_all(ctx);
+            if (!rc && e == cudaSuccess) rc = rs;
+        }
+        return rc ? rc : cuda_rc(e);
+    }
+};
 }  // namespace
 
 extern "C" {
 
 size_t mctq_host_staging_min_bytes(void) {
     // per stream: one input chunk + one f32-sized output chunk (LUT output of a 2-byte input is 2x larger) + parameter area
-    return kHostStreams * (kHostChunkBytesIn + 2 * kHostChunkBytesIn) + (4u << 20);
+    return kHostStreams * (kHostChunkBytesIn + 2 * kHostChunkBytesIn) + kParamAreaBytes;
+}
+
+int mctq_host_set_deferred(int device, int on) {
+    HostCtx* ctx;
+    int rc = host_ctx(device, &ctx);
+    if (rc) return rc;
+    if (ctx->deferred && !on) rc = sync_all(ctx);
+    ctx->deferred = on ? 1 : 0;
+    return rc;
+}
+
+int mctq_host_wait(int device) {
+    HostCtx* ctx;
+    int rc = host_ctx(device, &ctx);
+    if (rc) return rc;
+    return sync_all(ctx);
 }
 
 int mctq_fq_affine_host(const void* x_host, void* y_host, int64_t n, int x_dtype, const float* scale_host,
@@ -143,45 +239,35 @@ int mctq_fq_affine_host(const void* x_host, void* y_host, int64_t n, int x_dtype
                         void* staging_dev, size_t staging_bytes, int device) {
     if (!x_host || !y_host || !scale_host || !zp_host || !staging_dev || n < 0 || C < 1 || inner < 1) return MCTQ_E_BADARG;
     if (x_dtype < 0 || x_dtype > 2) return MCTQ_E_DTYPE;
-    if (staging_bytes < mctq_host_staging_min_bytes() || (size_t)C * 8 > (4u << 20)) return MCTQ_E_BADARG;
+    if (staging_bytes < mctq_host_staging_min_bytes() || (size_t)C * 4 > kRingArrayBytes) return MCTQ_E_BADARG;
     if (n == 0) return 0;
     HostCtx* ctx;
     int rc = host_ctx(device, &ctx);
     if (rc) return rc;
     const size_t es = dtype_size(x_dtype);
-    uint8_t* base = reinterpret_cast<uint8_t*>(staging_dev);
-    uint8_t* slots = base + (4u << 20);
+    HostCall call{ctx, reinterpret_cast<uint8_t*>(staging_dev)};
     const bool zc = zero_copy_ok(x_host, y_host, n, es);
+    const uint8_t* xb = reinterpret_cast<const uint8_t*>(x_host);
+    uint8_t* yb = reinterpret_cast<uint8_t*>(y_host);
     if (C == 1) {
         // per-tensor: parameters travel by value, nothing to upload
         const float s = scale_host[0];
         const int32_t z = zp_host[0];
-        if (zc) {
-            rc = mctq_fq_affine_scalar(x_host, y_host, nullptr, n, x_dtype, s, z, qmin, qmax, MCTQ_CODES_NONE, ctx->st[0]);
-            cudaError_t e2 = cudaStreamSynchronize(ctx->st[0]);
-            return rc ? rc : cuda_rc(e2);
-        }
-        return run_pipeline(ctx, slots, reinterpret_cast<const uint8_t*>(x_host), reinterpret_cast<uint8_t*>(y_host), n, es, es, false,
-                            [&](uint8_t* d_in, uint8_t* d_out, int64_t cnt, int64_t, cudaStream_t st) {
-                                return mctq_fq_affine_scalar(d_in, d_out, nullptr, cnt, x_dtype, s, z, qmin, qmax, MCTQ_CODES_NONE, st);
-                            });
+        return call.run(xb, yb, n, es, es, zc, [&](const uint8_t* d_in, uint8_t* d_out, int64_t cnt, int64_t, cudaStream_t st) {
+            return mctq_fq_affine_scalar(d_in, d_out, nullptr, cnt, x_dtype, s, z, qmin, qmax, MCTQ_CODES_NONE, st);
+        });
     }
-    float* d_scale = reinterpret_cast<float*>(base);
-    int32_t* d_zp = reinterpret_cast<int32_t*>(base + (2u << 20));
-    cudaError_t e = cudaMemcpyAsync(d_scale, scale_host, (size_t)C * 4, cudaMemcpyHostToDevice, ctx->st[0]);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaMemcpyAsync(d_zp, zp_host, (size_t)C * 4, cudaMemcpyHostToDevice, ctx->st[0]);
-    if (e != cudaSuccess) return (int)e;
-    if (zc) {
-        rc = mctq_fq_affine(x_host, y_host, nullptr, n, x_dtype, d_scale, d_zp, C, inner, 0, qmin, qmax, MCTQ_CODES_NONE, ctx->st[0]);
-        cudaError_t e2 = cudaStreamSynchronize(ctx->st[0]);
-        return rc ? rc : cuda_rc(e2);
-    }
-    return run_pipeline(ctx, slots, reinterpret_cast<const uint8_t*>(x_host), reinterpret_cast<uint8_t*>(y_host), n, es, es, true,
-                        [&](uint8_t* d_in, uint8_t* d_out, int64_t cnt, int64_t off, cudaStream_t st) {
-                            return mctq_fq_affine(d_in, d_out, nullptr, cnt, x_dtype, d_scale, d_zp, C, inner, off, qmin, qmax,
-                                                  MCTQ_CODES_NONE, st);
-                        });
+    if ((rc = call.begin_params())) return rc;
+    memcpy(call.h_entry, scale_host, (size_t)C * 4);
+    memcpy(call.h_entry + kRingArrayBytes, zp_host, (size_t)C * 4);
+    if ((rc = call.before_uploads()) || (rc = call.upload(0, (size_t)C * 4)) || (rc = call.upload(kRingArrayBytes, (size_t)C * 4)) ||
+        (rc = call.after_uploads()))
+        return rc;
+    const float* d_scale = reinterpret_cast<const float*>(call.d_entry);
+    const int32_t* d_zp = reinterpret_cast<const int32_t*>(call.d_entry + kRingArrayBytes);
+    return call.run(xb, yb, n, es, es, zc, [&](const uint8_t* d_in, uint8_t* d_out, int64_t cnt, int64_t off, cudaStream_t st) {
+        return mctq_fq_affine(d_in, d_out, nullptr, cnt, x_dtype, d_scale, d_zp, C, inner, off, qmin, qmax, MCTQ_CODES_NONE, st);
+    });
 }
 
 int mctq_fq_lut_host(const void* x_host, float* y_host, int64_t n, int x_dtype, const void* table_host, int K,
@@ -191,38 +277,31 @@ int mctq_fq_lut_host(const void* x_host, float* y_host, int64_t n, int x_dtype, 
     if (!scalar_mode && !thr_host) return MCTQ_E_BADARG;
     if (x_dtype < 0 || x_dtype > 2) return MCTQ_E_DTYPE;
     const size_t tbytes = mctq_lut_table_bytes(K);
-    if (!tbytes || tbytes > (1u << 20)) return MCTQ_E_LUT;
-    if (staging_bytes < mctq_host_staging_min_bytes() || (size_t)C * 4 > (2u << 20)) return MCTQ_E_BADARG;
+    if (!tbytes || tbytes > kRingTableBytes) return MCTQ_E_LUT;
+    if (staging_bytes < mctq_host_staging_min_bytes() || (size_t)C * 4 > kRingArrayBytes) return MCTQ_E_BADARG;
     if (n == 0) return 0;
     HostCtx* ctx;
     int rc = host_ctx(device, &ctx);
     if (rc) return rc;
     const size_t es = dtype_size(x_dtype);
-    uint8_t* base = reinterpret_cast<uint8_t*>(staging_dev);
-    float* d_thr = reinterpret_cast<float*>(base);
-    uint8_t* d_table = base + (2u << 20);
-    uint8_t* slots = base + (4u << 20);
-    cudaError_t e = cudaSuccess;
-    if (!scalar_mode) e = cudaMemcpyAsync(d_thr, thr_host, (size_t)C * 4, cudaMemcpyHostToDevice, ctx->st[0]);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaMemcpyAsync(d_table, table_host, tbytes, cudaMemcpyHostToDevice, ctx->st[0]);
-    if (e != cudaSuccess) return (int)e;
-    if (zero_copy_ok(x_host, y_host, n, es)) {
-        if (scalar_mode)
-            rc = mctq_fq_lut_scalar(x_host, y_host, nullptr, n, x_dtype, d_table, K, divisor, thr_f32, round_to_x_dtype, MCTQ_CODES_NONE, ctx->st[0]);
-        else
-            rc = mctq_fq_lut(x_host, y_host, nullptr, n, x_dtype, d_table, K, d_thr, C, inner, 0, eps, MCTQ_CODES_NONE, ctx->st[0]);
-        cudaError_t e2 = cudaStreamSynchronize(ctx->st[0]);
-        return rc ? rc : cuda_rc(e2);
-    }
-    return run_pipeline(ctx, slots, reinterpret_cast<const uint8_t*>(x_host), reinterpret_cast<uint8_t*>(y_host), n, es, 4, true,
-                        [&](uint8_t* d_in, uint8_t* d_out, int64_t cnt, int64_t off, cudaStream_t st) {
-                            float* out = reinterpret_cast<float*>(d_out);
-                            if (scalar_mode)
-                                return mctq_fq_lut_scalar(d_in, out, nullptr, cnt, x_dtype, d_table, K, divisor, thr_f32, round_to_x_dtype,
-                                                          MCTQ_CODES_NONE, st);
-                            return mctq_fq_lut(d_in, out, nullptr, cnt, x_dtype, d_table, K, d_thr, C, inner, off, eps, MCTQ_CODES_NONE, st);
-                        });
+    HostCall call{ctx, reinterpret_cast<uint8_t*>(staging_dev)};
+    if ((rc = call.begin_params())) return rc;
+    if (!scalar_mode) memcpy(call.h_entry, thr_host, (size_t)C * 4);
+    memcpy(call.h_entry + 2 * kRingArrayBytes, table_host, tbytes);
+    if ((rc = call.before_uploads())) return rc;
+    if (!scalar_mode && (rc = call.upload(0, (size_t)C * 4))) return rc;
+    if ((rc = call.upload(2 * kRingArrayBytes, tbytes)) || (rc = call.after_uploads())) return rc;
+    const float* d_thr = reinterpret_cast<const float*>(call.d_entry);
+    const uint8_t* d_table = call.d_entry + 2 * kRingArrayBytes;
+    const bool zc = zero_copy_ok(x_host, y_host, n, es);
+    return call.run(reinterpret_cast<const uint8_t*>(x_host), reinterpret_cast<uint8_t*>(y_host), n, es, 4, zc,
+                    [&](const uint8_t* d_in, uint8_t* d_out, int64_t cnt, int64_t off, cudaStream_t st) {
+                        float* out = reinterpret_cast<float*>(d_out);
+                        if (scalar_mode)
+                            return mctq_fq_lut_scalar(d_in, out, nullptr, cnt, x_dtype, d_table, K, divisor, thr_f32, round_to_x_dtype,
+                                                      MCTQ_CODES_NONE, st);
+                        return mctq_fq_lut(d_in, out, nullptr, cnt, x_dtype, d_table, K, d_thr, C, inner, off, eps, MCTQ_CODES_NONE, st);
+                    });
 }
 
 }  // extern "C"

@@ -550,6 +550,58 @@ def _lut_scalar_cuda(x, table, K, divisor, threshold, round_to_input_dtype):
 
 # --------------------------------------------------------------------------------------------- CPU-tensor impls
 # A host tensor is streamed through the GPU in chunks (pinned memory overlaps copies and kernels).
+class host_pipeline:
+    """Context manager: quantizer / holder / wrapper calls on HOST (pinned) tensors inside the block are only
+    *enqueued* -- their results are complete when the block exits.  The H2D -> kernel -> D2H pipeline then keeps
+    running across the tensors of a model instead of filling and draining once per call (mctq_host_set_deferred /
+    mctq_host_wait).  Inputs must not be modified inside the block; the block keeps them (and the outputs) alive.
+
+        with mct_quantizers_b200.host_pipeline():
+            outs = [holder(x) for holder, x in zip(holders, pinned_host_tensors)]
+        # outs are complete here
+    """
+    _active = {}          # device index -> innermost active scope
+
+    def __init__(self, device=None):
+        self._device = device
+        self._keep = []
+        self._outer = None
+
+    def __enter__(self):
+        dev = _require_cuda_for_host_path() if self._device is None else torch.device(self._device).index
+        self._dev = dev
+        self._outer = host_pipeline._active.get(dev)
+        if self._outer is None:
+            _native.check(_native.load().mctq_host_set_deferred(dev, 1), "mctq_host_set_deferred")
+        host_pipeline._active[dev] = self
+        return self
+
+    def wait(self):
+        """Complete everything enqueued so far (the block stays deferred)."""
+        _native.check(_native.load().mctq_host_wait(self._dev), "mctq_host_wait")
+        self._keep.clear()
+
+    def __exit__(self, *exc):
+        try:
+            if self._outer is None:
+                _native.check(_native.load().mctq_host_set_deferred(self._dev, 0), "mctq_host_set_deferred")   # waits
+            else:
+                self.wait()
+        finally:
+            self._keep.clear()
+            if self._outer is None:
+                host_pipeline._active.pop(self._dev, None)
+            else:
+                host_pipeline._active[self._dev] = self._outer
+        return False
+
+
+def _host_keepalive(dev, *tensors):
+    scope = host_pipeline._active.get(dev)
+    if scope is not None:
+        scope._keep.extend(tensors)
+
+
 def _affine_host(x, scale_np, zp_np, C, inner, quant_min, quant_max):
     dev = _require_cuda_for_host_path()
     tag = _dtype_tag(x)
@@ -562,6 +614,7 @@ def _affine_host(x, scale_np, zp_np, C, inner, quant_min, quant_max):
                                      zp_np.ctypes.data_as(c_vp), C, inner, int(quant_min), int(quant_max),
                                      _ptr(stg), stg.numel(), dev)
         _native.check(rc, "mctq_fq_affine_host")
+        _host_keepalive(dev, xc, y)
     return y
 
 
@@ -603,6 +656,7 @@ def _lut_host(x, table, K, thr_np, C, inner, eps, scalar_mode, divisor, thr_f32,
                                   float(np.float32(eps)), int(scalar_mode), float(np.float32(divisor)),
                                   float(np.float32(thr_f32)), int(round_flag), _ptr(stg), stg.numel(), dev)
         _native.check(rc, "mctq_fq_lut_host")
+        _host_keepalive(dev, xc, y)
     return y
 
 

@@ -474,6 +474,53 @@ def test_host_path_multi_chunk(Q):
     assert torch.equal(ql(x.clone()), ql(x.clone().to(DEV)).cpu())
 
 
+def test_host_pipeline_deferred_calls(Q, lib):
+    """host_pipeline(): calls on pinned host tensors are only enqueued and overlap with each other; every result is
+    complete at block exit and equals the device path.  More calls than parameter-ring entries, differing per-channel
+    parameters, small (zero-copy) and multi-chunk tensors, LUT and affine mixed, nested scope, explicit wait()."""
+    import mct_quantizers_b200 as mctq
+    g = torch.Generator().manual_seed(11)
+    jobs = []
+    for i in range(11):
+        rows = 5 + 3 * i
+        cols = (1 << 12) if i % 3 else (3 << 19) + 17            # 80 KB .. 70 MB
+        x = torch.empty(rows, cols, dtype=torch.float32).normal_(0, 1 + 0.1 * i, generator=g)
+        thr = [0.3 + 0.05 * ((7 * i + r) % 13) for r in range(rows)]
+        if i % 4 == 1:
+            q = Q.WeightsLUTSymmetricInferableQuantizer(4, [float(v) for v in range(-120, 120, 15)], thr, True, 0, 2)
+        elif i % 4 == 2:
+            q = Q.WeightsUniformInferableQuantizer(8, [-t for t in thr], [1.7 * t for t in thr], True, 0)
+        elif i % 4 == 3:
+            q = Q.ActivationUniformInferableQuantizer(8, [-1.0 - 0.1 * i], [2.3])
+        else:
+            q = Q.WeightsSymmetricInferableQuantizer(8, thr, True, 0)
+        if i == 5:
+            x = x.to(torch.bfloat16)
+        jobs.append((q, x))
+    want = [q(x.clone().to(DEV)).cpu() for q, x in jobs]
+    pinned = [x.clone().pin_memory() for _, x in jobs]
+    before = lib.mctq_launch_count()
+    with mctq.host_pipeline() as hp:
+        outs = [q(xp) for (q, _), xp in zip(jobs[:6], pinned[:6])]
+        hp.wait()
+        assert all(torch.equal(o, w) for o, w in zip(outs, want[:6]))
+        with mctq.host_pipeline():                               # nested scope: waits at its own exit, stays deferred
+            outs.append(jobs[6][0](pinned[6]))
+        assert torch.equal(outs[6], want[6])
+        outs += [q(xp) for (q, _), xp in zip(jobs[7:], pinned[7:])]
+    assert lib.mctq_launch_count() - before >= len(jobs)
+    for k, (o, w) in enumerate(zip(outs, want)):
+        assert o.device.type == "cpu" and o.is_pinned() and torch.equal(o, w), k
+    for xp, (_, x) in zip(pinned, jobs):
+        assert torch.equal(xp, x)                                # inputs untouched
+    # outside the block the calls synchronise again
+    assert torch.equal(jobs[0][0](pinned[0]), want[0])
+    # pageable tensors inside a block work too (their copies are synchronous by nature)
+    with mctq.host_pipeline():
+        o = jobs[2][0](jobs[2][1].clone())
+    assert torch.equal(o, want[2])
+
+
 def test_whole_model_single_launch(Q, lib):
     """quantize_model_weights: every affine weight quantizer of a model in ONE kernel == per-layer calls."""
     import mct_quantizers_b200 as mctq
