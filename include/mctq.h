@@ -234,8 +234,9 @@ int mctq_fq_lut_host(const void* x_host, float* y_host, int64_t n, int x_dtype,
 int64_t mctq_launch_count(void);
 /* variant selection for experiments: key 0 = unroll (0 = automatic [default], 2, 4, 8), key 1 = force rint path (0/1),
  * key 2 = force IEEE-division LUT path (0/1), key 3 = programmatic dependent launch (default 1),
- * key 4 = warp-shuffle search in the generic LUT kernel for tables of <= 32 entries (default 1); returns previous
- * value or <0 */
+ * key 4 = warp-shuffle search in the generic LUT kernel for tables of <= 32 entries (default 1),
+ * key 5 = wide vectors (8 elements per vector, 256-bit stores) in the kernels that have them (default 1);
+ * returns previous value or <0 */
 int mctq_set_tuning(int key, int value);
 /* device self-test of the 5-op correctly-rounded division used by the LUT kernels against __fdiv_rn
  * on n_pairs pseudo-random (x, d) pairs; *mismatches_dev (device int64) receives the number that differ */

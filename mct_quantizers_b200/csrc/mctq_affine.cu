@@ -109,11 +109,14 @@ template <bool RINT> struct AffineOp {
 // PREP: the per-channel parameters come from a prepared blob and are staged with 1-D TMA bulk copies (one elected thread,
 // one mbarrier) instead of per-thread load / divide / store loops -- the staging cost of a tile that touches hundreds
 // of channels (short rows, channel-innermost layouts) drops to a handful of instructions.
-template <typename T, int CHMODE, int CODE, int UNROLL, bool RINT, bool PREP>
+// VB: bytes per vector (16, or 8 for 2-byte types in CH_LAST mode: with 16-byte vectors of bf16 a lane needs 8 consecutive
+// parameter entries = two LDS.128 at a lane stride of 32 bytes, which is a 2-way bank conflict and made the kernel
+// shared-memory bound; 8-byte vectors need one LDS.128 per array at a lane stride of 16 bytes, conflict free).
+template <typename T, int CHMODE, int CODE, int UNROLL, bool RINT, bool PREP, int VB = 16>
 __global__ void __launch_bounds__(kThreads) fq_affine_kernel(const AffineArgs a) {
     using Op = AffineOp<RINT>;
-    constexpr int V = 16 / sizeof(T);
-    constexpr int WORDS = 4;
+    constexpr int V = VB / sizeof(T);
+    constexpr int WORDS = VB / 4;
     constexpr uint32_t TILE = kThreads * UNROLL * V;
     extern __shared__ __align__(16) float sm_par[];
     __shared__ Window sm_win;
@@ -140,7 +143,7 @@ __global__ void __launch_bounds__(kThreads) fq_affine_kernel(const AffineArgs a)
                 T tmp[V];
 #pragma unroll
                 for (int e = 0; e < V; ++e) tmp[e] = (l + e < remaining) ? xt[l + e] : from_f32<T>(0.0f);
-                memcpy(w[j], tmp, 16);
+                memcpy(w[j], tmp, VB);
             }
         }
     }
@@ -177,10 +180,8 @@ __global__ void __launch_bounds__(kThreads) fq_affine_kernel(const AffineArgs a)
                 if (n1 < a.W) bulk_g2s(sm_par + 4u * n1, a.prep_rec, (a.W - n1) * 16u, &sm_bar);
             }
         }
-        if (CHMODE == CH_LAST) {
-            base_mod = (uint32_t)((uint64_t)(a.elem_offset + t0) % a.period);
-            has_zp = __ldg(a.prep_flags) != 0;
-        }
+        if (CHMODE == CH_LAST) base_mod = (uint32_t)((uint64_t)(a.elem_offset + t0) % a.period);
+        if (CHMODE == CH_LAST || CHMODE == CH_ELEM) has_zp = __ldg(a.prep_flags) != 0;
         __syncthreads();                                               // barrier init + window visible to everyone
         if (CHMODE != CH_LAST) win = sm_win;
         mbar_wait(&sm_bar, 0);
@@ -222,15 +223,28 @@ __global__ void __launch_bounds__(kThreads) fq_affine_kernel(const AffineArgs a)
                 if (has_zp) *reinterpret_cast<float4*>(&pz[e]) = *reinterpret_cast<const float4*>(&sm_par[2 * a.period + i0 + e]);
                 else *reinterpret_cast<float4*>(&pz[e]) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
-#pragma unroll
-            for (int e = 0; e < V; ++e) {
+            if (!has_zp) {
                 typename Op::ChanParams p;
-                p.inv = pinv[e];
-                p.s = ps[e];
-                p.zp = __float_as_int(pz[e]);
-                if (RINT) { p.lo = (float)a.qmin; p.hi = (float)a.qmax; }
-                else { p.lo = (float)(a.qmin - p.zp); p.hi = (float)(a.qmax - p.zp); }
-                f[e] = Op::template apply<CODE != 0>(f[e], p, code[e]);
+                p.zp = 0;
+                p.lo = (float)a.qmin;
+                p.hi = (float)a.qmax;
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    p.inv = pinv[e];
+                    p.s = ps[e];
+                    f[e] = Op::template apply<CODE != 0>(f[e], p, code[e]);
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    typename Op::ChanParams p;
+                    p.inv = pinv[e];
+                    p.s = ps[e];
+                    p.zp = __float_as_int(pz[e]);
+                    if (RINT) { p.lo = (float)a.qmin; p.hi = (float)a.qmax; }
+                    else { p.lo = (float)(a.qmin - p.zp); p.hi = (float)(a.qmax - p.zp); }
+                    f[e] = Op::template apply<CODE != 0>(f[e], p, code[e]);
+                }
             }
         } else if (CHMODE == CH_VEC) {
             uint32_t slot, rem;
@@ -254,16 +268,32 @@ __global__ void __launch_bounds__(kThreads) fq_affine_kernel(const AffineArgs a)
             const uint32_t slot1 = (slot + 1 == a.W) ? 0u : slot + 1;
             const typename Op::ChanParams p0 = PREP ? Op::fetch_rec(sm_par, slot, a) : Op::fetch(sm_par, a.W, slot, a);
             const typename Op::ChanParams p1 = PREP ? Op::fetch_rec(sm_par, slot1, a) : Op::fetch(sm_par, a.W, slot1, a);
+            if (PREP && !has_zp) {
+                // all zero points are zero (symmetric quantizers): the clamp bounds are the same for every channel, only
+                // 1/s and s are selected per element
+                typename Op::ChanParams p = p0;
+                p.zp = 0;
+                p.lo = (float)a.qmin;
+                p.hi = (float)a.qmax;
 #pragma unroll
-            for (int e = 0; e < V; ++e) {
-                const bool first = (uint32_t)e < k;
-                typename Op::ChanParams p;
-                p.inv = first ? p0.inv : p1.inv;
-                p.s = first ? p0.s : p1.s;
-                p.lo = first ? p0.lo : p1.lo;
-                p.hi = first ? p0.hi : p1.hi;
-                p.zp = first ? p0.zp : p1.zp;
-                f[e] = Op::template apply<CODE != 0>(f[e], p, code[e]);
+                for (int e = 0; e < V; ++e) {
+                    const bool first = (uint32_t)e < k;
+                    p.inv = first ? p0.inv : p1.inv;
+                    p.s = first ? p0.s : p1.s;
+                    f[e] = Op::template apply<CODE != 0>(f[e], p, code[e]);
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    const bool first = (uint32_t)e < k;
+                    typename Op::ChanParams p;
+                    p.inv = first ? p0.inv : p1.inv;
+                    p.s = first ? p0.s : p1.s;
+                    p.lo = first ? p0.lo : p1.lo;
+                    p.hi = first ? p0.hi : p1.hi;
+                    p.zp = first ? p0.zp : p1.zp;
+                    f[e] = Op::template apply<CODE != 0>(f[e], p, code[e]);
+                }
             }
         } else {
             // rows shorter than a vector (inner < V, not channel-last): per-element parameter fetch
@@ -574,9 +604,14 @@ int check_codes(int32_t qmin, int32_t qmax, int code_mode, const void* codes) {
     return MCTQ_E_BADARG;
 }
 
-template <typename T, int CHMODE, int CODE, int UNROLL, bool RINT, bool PREP = false>
+// bytes per vector: 16, except channel-innermost layouts of 2-byte types (8: see fq_affine_kernel)
+template <typename T, int CHMODE> constexpr int vec_bytes() { return (CHMODE == CH_LAST && sizeof(T) == 2) ? 8 : 16; }
+
+template <typename T, int CHMODE, int CODE, int UNROLL_IN, bool RINT, bool PREP = false>
 int launch_affine_tiles(const AffineArgs& a_in, cudaStream_t st) {
-    constexpr int V = 16 / sizeof(T);
+    constexpr int VB = vec_bytes<T, CHMODE>();
+    constexpr int UNROLL = UNROLL_IN * 16 / VB;            // same bytes in flight per thread
+    constexpr int V = VB / sizeof(T);
     constexpr uint32_t TILE = kThreads * UNROLL * V;
     AffineArgs a = a_in;
     size_t smem = 0;
@@ -584,17 +619,17 @@ int launch_affine_tiles(const AffineArgs& a_in, cudaStream_t st) {
         a.div_W = make_fastdiv((uint32_t)a.C);
         a.div_period = make_fastdiv(a.period);
         smem = (size_t)a.period * 3 * sizeof(float);
-        int rc = ensure_smem(fq_affine_kernel<T, CHMODE, CODE, UNROLL, RINT, PREP>, smem);
+        int rc = ensure_smem(fq_affine_kernel<T, CHMODE, CODE, UNROLL, RINT, PREP, VB>, smem);
         if (rc) return rc;
     } else if (CHMODE != CH_PT) {
         set_window(a, TILE);
         smem = (size_t)a.W * (PREP ? 4 : 3) * sizeof(float);
-        int rc = ensure_smem(fq_affine_kernel<T, CHMODE, CODE, UNROLL, RINT, PREP>, smem);
+        int rc = ensure_smem(fq_affine_kernel<T, CHMODE, CODE, UNROLL, RINT, PREP, VB>, smem);
         if (rc) return rc;
     }
     int64_t tiles = (a.n + TILE - 1) / TILE;
     if (tiles > 0x7fffffffLL) return MCTQ_E_BADARG;
-    return launch_streaming(fq_affine_kernel<T, CHMODE, CODE, UNROLL, RINT, PREP>, (unsigned)tiles, smem, st, a);
+    return launch_streaming(fq_affine_kernel<T, CHMODE, CODE, UNROLL, RINT, PREP, VB>, (unsigned)tiles, smem, st, a);
 }
 
 // prepared parameters: TMA-staged variants (fast range, unroll 4, every code mode)
@@ -651,11 +686,12 @@ int launch_affine_typed(const AffineArgs& a, int code_mode, cudaStream_t st) {
     else if (a.inner % V == 0 && a.elem_offset % V == 0) chmode = CH_VEC;
     else {
         chmode = CH_ELEM;
-        if (a.inner == 1 && a.elem_offset % V == 0 && a.C <= 4096) {
-            // channel-innermost layout: one period of the channel pattern (lcm(C, V) entries, <= 48 KB) in shared memory
-            uint64_t g = (uint64_t)a.C, h = V;
+        constexpr int VL = vec_bytes<T, CH_LAST>() / sizeof(T);       // elements per vector in CH_LAST mode
+        if (a.inner == 1 && a.elem_offset % VL == 0 && a.C <= 4096) {
+            // channel-innermost layout: one period of the channel pattern (lcm(C, VL) entries, <= 48 KB) in shared memory
+            uint64_t g = (uint64_t)a.C, h = VL;
             while (h) { uint64_t t = g % h; g = h; h = t; }
-            const uint64_t period = (uint64_t)a.C / g * V;
+            const uint64_t period = (uint64_t)a.C / g * VL;
             if (period <= 4096) { chmode = CH_LAST; a2.period = (uint32_t)period; }
         }
     }

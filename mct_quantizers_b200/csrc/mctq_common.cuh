@@ -30,6 +30,7 @@ extern int g_unroll;
 extern int g_force_rint;
 extern int g_force_ieee_div;
 extern int g_lut_shfl;      // warp-shuffle search in the generic LUT kernel for tables of <= 32 entries (key 4)
+extern int g_wide;          // wide (8-element / 256-bit) vector variants (mctq_set_tuning key 5)
 extern int g_pdl;           // programmatic dependent launch for the streaming kernels (mctq_set_tuning key 3)
 
 enum ChMode { CH_PT = 0, CH_VEC = 1, CH_ELEM = 2, CH_LAST = 3 };
@@ -82,6 +83,17 @@ __device__ __forceinline__ void st_stream(uint32_t* p, const uint32_t& v) {
 }
 __device__ __forceinline__ void st_stream(uint16_t* p, const uint16_t& v) {
     asm volatile("st.global.L1::no_allocate.u16 [%0], %1;" :: "l"(p), "h"(v) : "memory");
+}
+
+// 256-bit streaming store (sm_100: STG.256): one instruction covers 32 contiguous bytes per lane, so a warp writes 1 KB of
+// contiguous memory -- two 128-bit stores per lane at a 32-byte lane stride would half-fill every sector twice
+__device__ __forceinline__ void st_stream256(void* p, const uint32_t* w) {
+    asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+}
+__device__ __forceinline__ void ld_stream256(const void* p, uint32_t* w) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(p));
 }
 
 // element <-> f32
@@ -292,6 +304,7 @@ int ensure_smem(K kernel, size_t bytes) {
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }
 
 // geometry of the channel window for a tile of `tile` elements
 template <class Args>

@@ -8,6 +8,7 @@ int g_force_rint = 0;
 int g_force_ieee_div = 0;
 int g_pdl = 1;
 int g_lut_shfl = 1;
+int g_wide = 1;             // 8-element vectors / 256-bit stores where a kernel has them (key 5)
 }  // namespace mctq
 
 using namespace mctq;
@@ -30,6 +31,7 @@ int mctq_set_tuning(int key, int value) {
         case 2: prev = g_force_ieee_div; g_force_ieee_div = value ? 1 : 0; return prev;
         case 3: prev = g_pdl; g_pdl = value ? 1 : 0; return prev;
         case 4: prev = g_lut_shfl; g_lut_shfl = value ? 1 : 0; return prev;
+        case 5: prev = g_wide; g_wide = value ? 1 : 0; return prev;
         default: return MCTQ_E_BADARG;
     }
 }

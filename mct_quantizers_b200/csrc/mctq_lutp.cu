@@ -151,11 +151,25 @@ __device__ __forceinline__ float fma_sat(float a, float b, float c) {
     return r;
 }
 
-template <typename T, int CHMODE, int CODE, int UNROLL>
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// V: elements per vector.  4 everywhere (8-byte loads of 2-byte types, one 16-byte f32 store), or 8 for 2-byte types when
+// the whole vector lies in one channel (CH_PT, CH_VEC with rows that are a multiple of 8): one 16-byte load, one 32-byte
+// store (STG.256), half the per-vector bookkeeping per element -- the 2-byte kernels are instruction-issue bound, not HBM bound.
+template <typename T, int CHMODE, int CODE, int UNROLL, int V>
 __global__ void __launch_bounds__(kThreads) fq_lutp_kernel(const LutPArgs a) {
-    constexpr int V = 4;
     constexpr int WORDS_IN = V * sizeof(T) / 4;
     constexpr uint32_t TILE = kThreads * UNROLL * V;
+    static_assert(V == 4 || (V == 8 && sizeof(T) == 2 && CHMODE != CH_ELEM), "vector width");
     extern __shared__ __align__(16) float sm_dyn[];                   // [records W * rec_floats][cells NC + 1 (+pad)][orig P]
     __shared__ Window sm_win;
     __shared__ __align__(8) uint64_t sm_bar;
@@ -221,10 +235,15 @@ __global__ void __launch_bounds__(kThreads) fq_lutp_kernel(const LutPArgs a) {
     if (CHMODE != CH_PT) win = sm_win;
     mbar_wait(&sm_bar, 0);
 
+    // Everything below addresses shared memory through 32-bit shared-window addresses: the element loop is
+    //   u = sat(x * s' + 0.5); cell = low bits of fma(u, NC, 1.5 * 2^23); b = cells[cell]          (candidate threshold)
+    //   px = rec + 4 b; X = [px]; y = [px + (x > X ? 4 P + 4 : 4 P)]                               (record = X[P] | Y[P] | s' ...)
     const float NCf = (float)a.NC;
     const uint32_t rec_bytes = (uint32_t)a.rec_floats * 4u;
     const uint32_t ybytes = (uint32_t)a.P * 4u;
-    const char* rec_base = reinterpret_cast<const char*>(sm_rec);
+    const uint32_t rec_base = smem_u32(sm_rec);
+    const uint32_t cells_s = smem_u32(sm_cells);
+    const uint32_t orig_s = smem_u32(sm_orig);
     float* yt = a.y + t0;
 #pragma unroll
     for (int j = 0; j < UNROLL; ++j) {
@@ -234,32 +253,34 @@ __global__ void __launch_bounds__(kThreads) fq_lutp_kernel(const LutPArgs a) {
         Pack<T, V>::unpack(w[j], f);
         uint32_t slot = 0, rem = 0;
         if (CHMODE != CH_PT) locate(l, win, a, slot, rem);
-        const char* rec = rec_base + slot * rec_bytes;
-        float sp = *reinterpret_cast<const float*>(rec + 2 * ybytes);
-        const float nan_probe = (f[0] + f[1]) + (f[2] + f[3]);     // NaN iff some element is NaN (or inf - inf)
+        uint32_t rec = rec_base + slot * rec_bytes;
+        float sp = lds_f32(rec + 2 * ybytes);
+        float nan_probe = f[0] + f[1];                             // NaN iff some element is NaN (or inf - inf)
+#pragma unroll
+        for (int e = 2; e < V; e += 2) nan_probe += f[e] + f[e + 1];
         // CH_ELEM: a vector of 4 straddles row boundaries.  Rows of at least 4 elements: at most one boundary, so the
         // record pointer / cell scale of the second row are selected per element; shorter rows advance per element.
         const bool two_rows = CHMODE == CH_ELEM && a.inner >= V;
         uint32_t k = V;                                             // elements of this vector in the first row
-        const char* rec1 = rec;
+        uint32_t rec1 = rec;
         float sp1 = sp;
         if (two_rows) {
             if (a.bigrow) {
                 const bool second = l >= win.split;
                 slot = second ? 1u : 0u;
                 rec = rec_base + slot * rec_bytes;
-                sp = *reinterpret_cast<const float*>(rec + 2 * ybytes);
+                sp = lds_f32(rec + 2 * ybytes);
                 k = second ? (uint32_t)V : min((uint32_t)V, win.split - l);
             } else {
                 k = a.div_inner.d - rem;
             }
             const uint32_t slot1 = (slot + 1 == a.W) ? 0u : slot + 1;
             rec1 = rec_base + slot1 * rec_bytes;
-            sp1 = *reinterpret_cast<const float*>(rec1 + 2 * ybytes);
+            sp1 = lds_f32(rec1 + 2 * ybytes);
         }
 #pragma unroll
         for (int e = 0; e < V; ++e) {
-            const char* r = rec;
+            uint32_t r = rec;
             float s = sp;
             if (CHMODE == CH_ELEM) {
                 if (two_rows) {
@@ -268,18 +289,19 @@ __global__ void __launch_bounds__(kThreads) fq_lutp_kernel(const LutPArgs a) {
                     s = first ? sp : sp1;
                 } else {
                     r = rec_base + slot * rec_bytes;
-                    s = *reinterpret_cast<const float*>(r + 2 * ybytes);
+                    s = lds_f32(r + 2 * ybytes);
                 }
             }
             const float x = f[e];
             const float u = fma_sat(x, s, 0.5f);                        // saturates to [0, 1]; NaN -> 0
             const float cf = __fmaf_rn(u, NCf, kMagicRound);            // integer cell index in the low mantissa bits
             const uint32_t cell = __float_as_uint(cf) & 0x1fffu;
-            const uint32_t b4 = (uint32_t)sm_cells[cell] << 2;          // byte offset of the candidate threshold
-            const float X = *reinterpret_cast<const float*>(r + b4);
-            const uint32_t p4 = b4 + ((x > X) ? 4u : 0u);
-            f[e] = *reinterpret_cast<const float*>(r + ybytes + p4);
-            if (CODE != 0) code[e] = sm_orig[p4 >> 2];
+            const uint32_t b = lds_u8(cells_s + cell);                  // index of the candidate threshold
+            const uint32_t px = r + (b << 2);
+            const float X = lds_f32(px);
+            const bool above = x > X;
+            f[e] = lds_f32(px + (above ? ybytes + 4u : ybytes));
+            if (CODE != 0) code[e] = (int)lds_u8(orig_s + b + (above ? 1u : 0u));
             if (CHMODE == CH_ELEM && !two_rows) {
                 if (++rem == a.div_inner.d) { rem = 0; slot = (slot + 1 == a.W) ? 0 : slot + 1; }
             }
@@ -297,8 +319,8 @@ __global__ void __launch_bounds__(kThreads) fq_lutp_kernel(const LutPArgs a) {
                     slot2 = jrow >= a.W ? jrow - a.W : jrow;
                 }
                 if (g[e] != g[e]) {
-                    f[e] = *reinterpret_cast<const float*>(rec_base + slot2 * rec_bytes + ybytes + 4u * pos0);
-                    if (CODE != 0) code[e] = sm_orig[pos0];
+                    f[e] = lds_f32(rec_base + slot2 * rec_bytes + ybytes + 4u * pos0);
+                    if (CODE != 0) code[e] = (int)lds_u8(orig_s + pos0);
                 }
                 if (CHMODE == CH_ELEM && !a.bigrow) {
                     if (++rem2 == a.div_inner.d) { rem2 = 0; slot2 = (slot2 + 1 == a.W) ? 0 : slot2 + 1; }
@@ -306,7 +328,12 @@ __global__ void __launch_bounds__(kThreads) fq_lutp_kernel(const LutPArgs a) {
             }
         }
         if (full || (int64_t)l + V <= remaining) {
-            if (a.y) { uint32_t o[4]; Pack<float, V>::pack(f, o); st_words<4>(yt + l, o); }
+            if (a.y) {
+                uint32_t o[V];
+                Pack<float, V>::pack(f, o);
+                if (V == 8) st_stream256(yt + l, o);        // 32 contiguous bytes per lane in one store
+                else st_words<4>(yt + l, o);
+            }
             if (CODE != 0) st_codes<V, CODE>(a.idx, t0 + l, code);
         } else if ((int64_t)l < remaining) {
             const int cnt = (int)(remaining - l);
@@ -335,38 +362,46 @@ using namespace mctq;
 
 namespace {
 
-template <typename T, int CHMODE, int CODE>
+template <typename T, int CHMODE, int CODE, int V>
 int launch_lutp_tiles(const LutPArgs& a_in, cudaStream_t st) {
     constexpr int UNROLL = 4;
-    constexpr uint32_t TILE = kThreads * UNROLL * 4;
+    constexpr uint32_t TILE = kThreads * UNROLL * V;
     LutPArgs a = a_in;
     uint32_t W = 1;
     if (CHMODE != CH_PT) { set_window(a, TILE); W = a.W; }
     size_t smem = (size_t)W * a.rec_floats * 4 + (((size_t)a.NC + 1 + 15) & ~(size_t)15) + (((size_t)a.P + 15) & ~(size_t)15);
     if (smem > 64 * 1024) return MCTQ_E_RANGE;            // caller falls back to the generic kernel
-    int rc = ensure_smem(fq_lutp_kernel<T, CHMODE, CODE, UNROLL>, smem);
+    int rc = ensure_smem(fq_lutp_kernel<T, CHMODE, CODE, UNROLL, V>, smem);
     if (rc) return rc;
     int64_t tiles = (a.n + TILE - 1) / TILE;
     if (tiles > 0x7fffffffLL) return MCTQ_E_BADARG;
-    return launch_streaming(fq_lutp_kernel<T, CHMODE, CODE, UNROLL>, (unsigned)tiles, smem, st, a);
+    return launch_streaming(fq_lutp_kernel<T, CHMODE, CODE, UNROLL, V>, (unsigned)tiles, smem, st, a);
+}
+
+template <typename T, int CHMODE, int V>
+int launch_lutp_code(const LutPArgs& a, int idx_mode, cudaStream_t st) {
+    switch (idx_mode) {
+        case MCTQ_CODES_INT8: return launch_lutp_tiles<T, CHMODE, MCTQ_CODES_INT8, V>(a, st);
+        case MCTQ_CODES_INT4: return launch_lutp_tiles<T, CHMODE, MCTQ_CODES_INT4, V>(a, st);
+        default: return launch_lutp_tiles<T, CHMODE, MCTQ_CODES_NONE, V>(a, st);
+    }
 }
 
 template <typename T>
 int launch_lutp_typed(const LutPArgs& a, int idx_mode, cudaStream_t st) {
-    int chmode;
-    if (a.C == 1) chmode = CH_PT;
-    else if (a.inner % 4 == 0 && a.elem_offset % 4 == 0) chmode = CH_VEC;
-    else chmode = CH_ELEM;
-#define MCTQ_DISPATCH_LUTP(CM)                                                             \
-    switch (idx_mode) {                                                                    \
-        case MCTQ_CODES_INT8: return launch_lutp_tiles<T, CM, MCTQ_CODES_INT8>(a, st);     \
-        case MCTQ_CODES_INT4: return launch_lutp_tiles<T, CM, MCTQ_CODES_INT4>(a, st);     \
-        default: return launch_lutp_tiles<T, CM, MCTQ_CODES_NONE>(a, st);                  \
+    // 8-element vectors for 2-byte inputs: 16-byte aligned x, 8-byte aligned int8 indices, rows a multiple of 8
+    bool v8 = g_wide && sizeof(T) == 2 && aligned16(a.x) && (!a.y || aligned32(a.y)) &&
+              (idx_mode != MCTQ_CODES_INT8 || (reinterpret_cast<uintptr_t>(a.idx) & 7u) == 0);
+    if (a.C == 1) {
+        if (sizeof(T) == 2 && v8) return launch_lutp_code<T, CH_PT, sizeof(T) == 2 ? 8 : 4>(a, idx_mode, st);
+        return launch_lutp_code<T, CH_PT, 4>(a, idx_mode, st);
     }
-    if (chmode == CH_PT) { MCTQ_DISPATCH_LUTP(CH_PT) }
-    if (chmode == CH_VEC) { MCTQ_DISPATCH_LUTP(CH_VEC) }
-    MCTQ_DISPATCH_LUTP(CH_ELEM)
-#undef MCTQ_DISPATCH_LUTP
+    if (a.inner % 4 == 0 && a.elem_offset % 4 == 0) {
+        v8 = v8 && a.inner % 8 == 0 && a.elem_offset % 8 == 0;
+        if (sizeof(T) == 2 && v8) return launch_lutp_code<T, CH_VEC, sizeof(T) == 2 ? 8 : 4>(a, idx_mode, st);
+        return launch_lutp_code<T, CH_VEC, 4>(a, idx_mode, st);
+    }
+    return launch_lutp_code<T, CH_ELEM, 4>(a, idx_mode, st);
 }
 
 }  // namespace

@@ -49,8 +49,12 @@ def main():
     ap.add_argument("--unroll", default="0", help="0 = the library default (automatic)")
     ap.add_argument("--dtypes", default="f32,bf16")
     ap.add_argument("--json", default=None)
+    ap.add_argument("--tune", default="", help="comma separated key=value pairs for mctq_set_tuning (experiments)")
     args = ap.parse_args()
     lib = _native.load(build_if_missing=False)
+    for kv in filter(None, args.tune.split(",")):
+        k, v = kv.split("=")
+        assert lib.mctq_set_tuning(int(k), int(v)) >= 0
     dev = torch.device("cuda:0")
     stream = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)  # noqa: E731
     peak = 6457.7

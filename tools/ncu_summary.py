@@ -95,12 +95,15 @@ def variants(path, order_path):
     print(f"# ncu --set full, one launch per kernel variant ({path})\n")
     print("`alg GB/s` = algorithmic bytes / gpu__time_duration of the profiled (cold, serialised) launch; `traffic/alg` = "
           "(dram read + write) / algorithmic bytes.\n")
-    print("| # | variant | kernel | us | alg GB/s | dram R GB | dram W GB | traffic/alg | dram % peak | issue active % | warps active % | regs |")
-    print("|---:|---|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|")
+    print("`instr/elem` = 32 x smsp__inst_executed.sum / elements (thread-level instructions per tensor element); `smem conflicts` = "
+          "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum per 1000 elements.\n")
+    print("| # | variant | kernel | us | alg GB/s | dram R GB | dram W GB | traffic/alg | dram % peak | issue active % | warps active % | regs | instr/elem | smem conflicts |")
+    print("|---:|---|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|")
     data = rows[2:]
     for i, r in enumerate(data):
         lab = order[i]["label"] if i < len(order) else "?"
         alg = order[i]["algorithmic_bytes"] if i < len(order) else float("nan")
+        ne = order[i].get("elements", float("nan")) if i < len(order) else float("nan")
         us = _scaled(r[col["gpu__time_duration.sum"]], units[col["gpu__time_duration.sum"]], t_unit)
         rd = _scaled(r[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]], b_unit)
         wr = _scaled(r[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]], b_unit)
@@ -108,7 +111,9 @@ def variants(path, order_path):
         print(f"| {i} | {lab} | `{short(r[col['Kernel Name']])[:60]}` | {us:.1f} | {alg / us / 1e3:.0f} | {rd / 1e9:.3f} | {wr / 1e9:.3f} | "
               f"{(rd + wr) / alg:.3f} | {_num(g('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed')):.1f} | "
               f"{_num(g('smsp__issue_active.avg.pct_of_peak_sustained_active')):.1f} | "
-              f"{_num(g('sm__warps_active.avg.pct_of_peak_sustained_active')):.1f} | {g('launch__registers_per_thread')} |")
+              f"{_num(g('sm__warps_active.avg.pct_of_peak_sustained_active')):.1f} | {g('launch__registers_per_thread')} | "
+              f"{32 * _num(g('smsp__inst_executed.sum')) / ne:.1f} | "
+              f"{1000 * _num(g('l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum')) / ne:.1f} |")
 
 
 def traffic(path):

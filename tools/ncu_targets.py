@@ -51,7 +51,7 @@ def main():
         xl = torch.empty(n, dtype=tdt, device=dev).normal_(0, 0.02)
 
         def add(label, nbytes, fn):
-            jobs.append((f"{label} [{dt}]", int(nbytes), fn))
+            jobs.append((f"{label} [{dt}]", int(nbytes), fn, n))
 
         add("affine per-tensor scalar qparams (ActivationSymmetric/POT/Uniform)", 2 * n * es,
             lambda x=x, y=y, n=n, tag=tag: lib.mctq_fq_affine_scalar(vp(x), vp(y), None, n, tag, 0.0129, 77, 0, 255, 0, st()))
@@ -62,11 +62,33 @@ def main():
             add(f"affine {label}", 2 * n * es,
                 lambda x=x, y=y, n=n, tag=tag, sc=sc, zp=zp, C=C, inner=inner:
                 lib.mctq_fq_affine(vp(x), vp(y), None, n, tag, vp(sc), vp(zp), C, inner, 0, -128, 127, 0, st()))
+            nb = lib.mctq_affine_prepared_bytes(C)
+            blob = torch.empty(nb, dtype=torch.uint8, device=dev)
+            rc = lib.mctq_affine_prepare(vp(sc), vp(zp), C, vp(blob), nb, st())
+            assert rc == 0, rc
+            add(f"affine-prepared {label} (TMA-staged parameters)", 2 * n * es,
+                lambda x=x, y=y, n=n, tag=tag, blob=blob, C=C, inner=inner:
+                lib.mctq_fq_affine_prepared(vp(x), vp(y), None, n, tag, vp(blob), C, inner, 0, -128, 127, 0, st()))
+        for pre, label in ((_native.PRE_RELU, "relu"), (_native.PRE_ADD_RELU, "add+relu")):
+            other = y if pre == _native.PRE_ADD_RELU else None
+            yo = torch.empty(n, dtype=tdt, device=dev) if other is not None else y
+            add(f"fused {label} -> affine per-tensor", (3 if other is not None else 2) * n * es,
+                lambda x=x, yo=yo, other=other, n=n, tag=tag, pre=pre:
+                lib.mctq_fq_affine_scalar_pre(vp(x), vp(other), vp(yo), n, tag, pre, 0.0235, 0, 0, 255, st()))
+        if es == 4:
+            sc1 = torch.full((1,), 0.03125, device=dev)
+            zp1 = torch.zeros(1, dtype=torch.int32, device=dev)
+            scC = torch.rand(4096, device=dev) * 0.05 + 0.01
+            zpC = torch.zeros(4096, dtype=torch.int32, device=dev)
+            add("dequant int8 codes -> f32 per-tensor", n * 5,
+                lambda codes=codes, y=y, n=n: lib.mctq_dequant_affine(vp(codes), 1, 1, vp(y), n, vp(sc1), vp(zp1), 1, 1, 0, st()))
+            add("dequant int4 codes -> f32 per-channel rows 11008", n * 4.5,
+                lambda codes=codes, y=y, n=n: lib.mctq_dequant_affine(vp(codes), 2, 1, vp(y), n, vp(scC), vp(zpC), 4096, 11008, 0, st()))
         add("affine per-tensor + int8 codes", n * (2 * es + 1),
             lambda x=x, y=y, n=n, tag=tag, codes=codes: lib.mctq_fq_affine_scalar(vp(x), vp(y), vp(codes), n, tag, 0.03125, 0, -128, 127, 1, st()))
         add("affine per-tensor int4 codes only", n * (es + 0.5),
             lambda x=x, n=n, tag=tag, codes=codes: lib.mctq_fq_affine_scalar(vp(x), None, vp(codes), n, tag, 0.5, 0, -8, 7, 2, st()))
-        for (C, inner, label) in ((4096, 11008, "rows 11008"), (1, 1, "per-tensor")):
+        for (C, inner, label) in ((4096, 11008, "rows 11008"), (4096, 64, "rows 64"), (1, 1, "per-tensor")):
             thr = torch.rand(C, device=dev) * 0.05 + 0.06
             nb = lib.mctq_lut_prepared_bytes(16, 8, 1, C)
             blob = torch.empty(nb, dtype=torch.uint8, device=dev)
@@ -75,7 +97,7 @@ def main():
             add(f"lut-prepared K=16 {label}", n * (es + 4),
                 lambda xl=xl, yf=yf, n=n, tag=tag, blob=blob, C=C, inner=inner:
                 lib.mctq_fq_lut_prepared(vp(xl), vp(yf), None, n, tag, vp(blob), 16, 8, 1, C, inner, 0, 0, st()))
-            if C > 1:
+            if inner > 64:
                 add(f"lut-prepared K=16 {label} + int4 indices", n * (es + 4.5),
                     lambda xl=xl, yf=yf, n=n, tag=tag, blob=blob, C=C, inner=inner, codes=codes:
                     lib.mctq_fq_lut_prepared(vp(xl), vp(yf), vp(codes), n, tag, vp(blob), 16, 8, 1, C, inner, 0, 2, st()))
@@ -84,18 +106,18 @@ def main():
                     lib.mctq_fq_lut(vp(xl), vp(yf), None, n, tag, vp(table_dev), 16, vp(thr), C, inner, 0, 1e-8, 0, st()))
 
     torch.cuda.synchronize()
-    for _, _, fn in jobs:          # warm-up (module load, shared-memory attributes) outside the profiled range
+    for _, _, fn, _ in jobs:          # warm-up (module load, shared-memory attributes) outside the profiled range
         rc = fn()
         assert rc == 0, rc
     torch.cuda.synchronize()
     torch.cuda.profiler.start()
-    for _, _, fn in jobs:
+    for _, _, fn, _ in jobs:
         fn()
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
     os.makedirs(os.path.dirname(args.order) or ".", exist_ok=True)
     with open(args.order, "w") as f:
-        json.dump([{"label": lab, "algorithmic_bytes": nb} for lab, nb, _ in jobs], f, indent=1)
+        json.dump([{"label": lab, "algorithmic_bytes": nb, "elements": ne} for lab, nb, _, ne in jobs], f, indent=1)
     print(f"{len(jobs)} launches profiled")
 
 
