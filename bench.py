@@ -443,14 +443,18 @@ def run_b200(args):
         achieved = n_a * BYTES_PER_ELEM / (act_ms / args.steps * 1e-3) / 1e9
         # dram bytes per launch of the dominant kernel: from the committed ncu capture of this same command
         # (profiles/r01_bench_traffic.json, made by tools/ncu_summary.py traffic); only valid for the default batch
-        traffic, traffic_src = None, None
+        traffic, traffic_src, kname = None, None, None
         try:
             if args.batch == 256:
-                with open(os.path.join(ROOT, "profiles", "r01_bench_traffic.json")) as f:
+                import glob
+                cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_bench_traffic.json")))
+                with open(cands[-1]) as f:                       # the newest round's capture
                     for k, v in json.load(f).items():
-                        if k.startswith("fq_affine_kernel<float, 0, 0, 4"):
+                        if k.startswith("fq_affine_kernel<float, 0, 0,"):       # <float, CH_PT, no codes, ...>
                             traffic = int(v["dram_bytes_per_launch"])
-                            traffic_src = "profiles/r01_bench_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the 53 launches of a step)"
+                            kname = k
+                            traffic_src = ("profiles/%s (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the 53 launches "
+                                           "of a step)" % os.path.basename(cands[-1]))
         except Exception:
             pass
         line = {"metric": METRIC, "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
@@ -467,7 +471,8 @@ def run_b200(args):
                 "pct_of_8TBs": round(100 * value / world / 8000.0, 2),
                 "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                              "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                             "kernel": "fq_affine_kernel<float, CH_PT, no codes, unroll 4> (ActivationUniform sites)",
+                             "kernel": "%s = fq_affine_kernel<T, CH_PT, no codes, unroll 2 (8 KB tiles), fast rounding, by-value "
+                                       "parameters, 16-byte vectors> (ActivationUniform sites)" % (kname or "fq_affine_kernel<float, 0, 0, 2, false, false, 16>"),
                              "launches_per_step": len(acts),
                              "avg_launch_us": round(act_ms / args.steps / len(acts) * 1e3, 2),
                              "how": "CUDA events around every timed step minus the weights launch (%.1f us, timed separately)" % (w_ms * 1e3),

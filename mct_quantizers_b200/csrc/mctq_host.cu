@@ -1,4 +1,6 @@
 // mctq_host.cu -- process-wide state, introspection entry points and the host-buffer (staged) operators.
+#include <mutex>
+
 #include "mctq_common.cuh"
 
 namespace mctq {
@@ -61,6 +63,7 @@ struct HostCtx {
     uint8_t* pin = nullptr;                          // pinned host mirror of the parameter ring
     cudaEvent_t uploaded[kRing] = {};                // the H2D copy out of pin entry e has finished
     cudaEvent_t released[kRing][kHostStreams] = {};  // the last kernel of stream i that reads device entry e has finished
+    std::mutex mu;                                   // host-buffer calls of one device are serialised (ctypes drops the GIL)
 };
 HostCtx g_hctx[16];
 
@@ -69,6 +72,7 @@ int host_ctx(int device, HostCtx** out) {
     HostCtx& c = g_hctx[device];
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return (int)e;
+    std::lock_guard<std::mutex> init_lock(c.mu);
     if (c.device != device) {
         for (int i = 0; i < kHostStreams; ++i) {
             e = cudaStreamCreateWithFlags(&c.st[i], cudaStreamNonBlocking);
@@ -117,18 +121,21 @@ int64_t pick_chunk_elems(int64_t n, size_t in_elem_bytes, size_t slot_elem_bytes
 }
 
 // Small tensors in PINNED host memory skip the staging pipeline altogether: the streaming kernel reads x and writes y
-// directly over PCIe through their unified virtual addresses (one launch, one synchronise, no fill / drain of a
-// three-stage pipeline).  Measured on the B200 box: 4 MB 0.215 -> 0.168 ms, 1 MB 0.055 ms; above ~16 MB the copy engines
-// win (92 vs 80 GB/s at 1 GB), so the cut-over is 8 MB of input.
-constexpr size_t kZeroCopyMaxBytesIn = 8u << 20;
+// directly over PCIe through their unified virtual addresses (one launch, no fill / drain of a three-stage pipeline).
+// Measured on the B200 box (profiles/r01_pcie_probe.txt), one synchronous call: 1 MB 40, 4 MB 50 vs 41, 17 MB 60 vs 51,
+// 67 MB 69 vs 74, 1 GB 79 vs 88-93 GB/s (zero-copy vs copy engines) -> cut-over at 32 MB of input.  In deferred mode the
+// pipeline does not drain between calls, so the copy engines win earlier: cut-over at 8 MB.
+constexpr size_t kZeroCopyMaxBytesSync = 32u << 20;
+constexpr size_t kZeroCopyMaxBytesDeferred = 8u << 20;
 
 bool is_pinned(const void* p) {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
     return at.type == cudaMemoryTypeHost && at.devicePointer == p;
 }
-bool zero_copy_ok(const void* x_host, const void* y_host, int64_t n, size_t in_es) {
-    return (size_t)n * in_es <= kZeroCopyMaxBytesIn && is_pinned(x_host) && is_pinned(y_host);
+bool zero_copy_ok(const HostCtx* ctx, const void* x_host, const void* y_host, int64_t n, size_t in_es) {
+    const size_t limit = ctx->deferred ? kZeroCopyMaxBytesDeferred : kZeroCopyMaxBytesSync;
+    return (size_t)n * in_es <= limit && is_pinned(x_host) && is_pinned(y_host);
 }
 
 // One host-buffer call.  Parameters (if any) go through ring entry `e` of the pinned mirror and the device parameter
@@ -224,6 +231,7 @@ int mctq_host_set_deferred(int device, int on) {
     HostCtx* ctx;
     int rc = host_ctx(device, &ctx);
     if (rc) return rc;
+    std::lock_guard<std::mutex> lock(ctx->mu);
     if (ctx->deferred && !on) rc = sync_all(ctx);
     ctx->deferred = on ? 1 : 0;
     return rc;
@@ -233,6 +241,7 @@ int mctq_host_wait(int device) {
     HostCtx* ctx;
     int rc = host_ctx(device, &ctx);
     if (rc) return rc;
+    std::lock_guard<std::mutex> lock(ctx->mu);
     return sync_all(ctx);
 }
 
@@ -246,9 +255,10 @@ int mctq_fq_affine_host(const void* x_host, void* y_host, int64_t n, int x_dtype
     HostCtx* ctx;
     int rc = host_ctx(device, &ctx);
     if (rc) return rc;
+    std::lock_guard<std::mutex> lock(ctx->mu);
     const size_t es = dtype_size(x_dtype);
     HostCall call{ctx, reinterpret_cast<uint8_t*>(staging_dev)};
-    const bool zc = zero_copy_ok(x_host, y_host, n, es);
+    const bool zc = zero_copy_ok(ctx, x_host, y_host, n, es);
     const uint8_t* xb = reinterpret_cast<const uint8_t*>(x_host);
     uint8_t* yb = reinterpret_cast<uint8_t*>(y_host);
     if (C == 1) {
@@ -285,6 +295,7 @@ int mctq_fq_lut_host(const void* x_host, float* y_host, int64_t n, int x_dtype, 
     HostCtx* ctx;
     int rc = host_ctx(device, &ctx);
     if (rc) return rc;
+    std::lock_guard<std::mutex> lock(ctx->mu);
     const size_t es = dtype_size(x_dtype);
     HostCall call{ctx, reinterpret_cast<uint8_t*>(staging_dev)};
     if ((rc = call.begin_params())) return rc;
@@ -295,7 +306,7 @@ int mctq_fq_lut_host(const void* x_host, float* y_host, int64_t n, int x_dtype, 
     if ((rc = call.upload(2 * kRingArrayBytes, tbytes)) || (rc = call.after_uploads())) return rc;
     const float* d_thr = reinterpret_cast<const float*>(call.d_entry);
     const uint8_t* d_table = call.d_entry + 2 * kRingArrayBytes;
-    const bool zc = zero_copy_ok(x_host, y_host, n, es);
+    const bool zc = zero_copy_ok(ctx, x_host, y_host, n, es);
     return call.run(reinterpret_cast<const uint8_t*>(x_host), reinterpret_cast<uint8_t*>(y_host), n, es, 4, zc,
                     [&](const uint8_t* d_in, uint8_t* d_out, int64_t cnt, int64_t off, cudaStream_t st) {
                         float* out = reinterpret_cast<float*>(d_out);
