@@ -202,6 +202,30 @@ int mctq_fq_lut_prepared(const void* x, float* y, void* idx, int64_t n, int x_dt
                          int lut_values_bitwidth, int is_signed, int64_t C, int64_t inner, int64_t elem_offset,
                          int idx_mode, void* stream);
 
+/* Whole-model LUT weight quantization in ONE launch (the LUT counterpart of mctq_fq_affine_multi; replaces the per-layer
+ * loop mct_quantizers/pytorch/quantize_wrapper.py:228-240 over weights_lut_symmetric_inferable_quantizer.py:89-128 /
+ * weights_lut_pot_inferable_quantizer.py:74-104 calls).  Every tensor brings its own prepared blob (mctq_lut_prepare).
+ * mctq_lut_multi_plan compiles the HOST descriptor array into an opaque plan blob of
+ * mctq_lut_multi_plan_bytes(descs, n_desc) bytes in HOST memory (returns the number of CTAs of the launch, or < 0:
+ * MCTQ_E_RANGE / MCTQ_E_BADARG mean "this tensor needs the single-tensor / generic entry point").  The launch passes the
+ * per-tensor argument blocks as kernel parameters (one launch per 180 tensors), so there is no device-side copy of the plan.
+ * x, y and the prepared blobs must stay valid while the plan is in use. */
+typedef struct MctqLutTensorDesc {
+    const void* x;            /* device, dtype below, 16-byte aligned */
+    float* y;                 /* device f32, 16-byte aligned */
+    const void* prepared_dev; /* mctq_lut_prepare blob of this tensor's quantizer */
+    int64_t n;
+    int64_t C;
+    int64_t inner;
+    int32_t dtype;
+    int32_t K;
+    int32_t lut_values_bitwidth;
+    int32_t is_signed;
+} MctqLutTensorDesc;
+size_t mctq_lut_multi_plan_bytes(const MctqLutTensorDesc* descs_host, int n_desc);   /* 0: some tensor is not plannable */
+int64_t mctq_lut_multi_plan(const MctqLutTensorDesc* descs_host, int n_desc, void* plan_host_out, size_t plan_bytes);
+int mctq_fq_lut_prepared_multi(const void* plan_host, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------
  * Host-buffer entry points: the same operators for tensors that live in HOST memory (pinned memory
  * overlaps; pageable memory works but serialises).  The data is streamed through `staging_dev`
@@ -235,7 +259,8 @@ int64_t mctq_launch_count(void);
 /* variant selection for experiments: key 0 = unroll (0 = automatic [default], 2, 4, 8), key 1 = force rint path (0/1),
  * key 2 = force IEEE-division LUT path (0/1), key 3 = programmatic dependent launch (default 1),
  * key 4 = warp-shuffle search in the generic LUT kernel for tables of <= 32 entries (default 1),
- * key 5 = wide vectors (8 elements per vector, 256-bit stores) in the kernels that have them (default 1);
+ * key 5 = wide vectors (8 elements per vector, 256-bit stores) in the kernels that have them (default 1),
+ * key 6 = tiles per CTA of the multi-tensor LUT launch, 1 or 4 (default 4; read by mctq_lut_multi_plan);
  * returns previous value or <0 */
 int mctq_set_tuning(int key, int value);
 /* device self-test of the 5-op correctly-rounded division used by the LUT kernels against __fdiv_rn

@@ -29,6 +29,12 @@ class MctqTensorDesc(ctypes.Structure):
                 ("qmin", c_i32), ("qmax", c_i32), ("dtype", c_i32), ("code_mode", c_i32)]
 
 
+class MctqLutTensorDesc(ctypes.Structure):
+    """Mirror of `struct MctqLutTensorDesc` (include/mctq.h)."""
+    _fields_ = [("x", c_vp), ("y", c_vp), ("prepared_dev", c_vp), ("n", c_i64), ("C", c_i64), ("inner", c_i64),
+                ("dtype", c_i32), ("K", c_i32), ("lut_values_bitwidth", c_i32), ("is_signed", c_i32)]
+
+
 # name -> (restype, argtypes): every symbol include/mctq.h declares
 SIGNATURES = {
     "mctq_abi_version": (c_int, []),
@@ -50,6 +56,9 @@ SIGNATURES = {
     "mctq_lut_prepared_bytes": (c_sz, [c_int, c_int, c_int, c_i64]),
     "mctq_lut_prepare": (c_int, [c_vp, c_int, c_vp, c_i64, c_f32, c_int, c_f32, c_f32, c_int, c_vp, c_sz, c_vp]),
     "mctq_fq_lut_prepared": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_int, c_int, c_i64, c_i64, c_i64, c_int, c_vp]),
+    "mctq_lut_multi_plan_bytes": (c_sz, [c_vp, c_int]),
+    "mctq_lut_multi_plan": (c_i64, [c_vp, c_int, c_vp, c_sz]),
+    "mctq_fq_lut_prepared_multi": (c_int, [c_vp, c_vp]),
     "mctq_host_staging_min_bytes": (c_sz, []),
     "mctq_host_set_deferred": (c_int, [c_int, c_int]),
     "mctq_host_wait": (c_int, [c_int]),
@@ -116,6 +125,11 @@ def load(build_if_missing=True):
             fn.argtypes = args
         if handle.mctq_abi_version() != 1:
             raise MctqError(f"ABI version mismatch: library reports {handle.mctq_abi_version()}, binding expects 1")
+        # experiments: MCTQ_TUNE="key=value,..." applies mctq_set_tuning at load time (see include/mctq.h)
+        for kv in filter(None, os.environ.get("MCTQ_TUNE", "").split(",")):
+            k, v = kv.split("=")
+            if handle.mctq_set_tuning(int(k), int(v)) < 0:
+                raise MctqError(f"MCTQ_TUNE: mctq_set_tuning({k}, {v}) rejected")
         _lib = handle
     return _lib
 

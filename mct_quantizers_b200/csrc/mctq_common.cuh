@@ -31,6 +31,7 @@ extern int g_force_rint;
 extern int g_force_ieee_div;
 extern int g_lut_shfl;      // warp-shuffle search in the generic LUT kernel for tables of <= 32 entries (key 4)
 extern int g_wide;          // wide (8-element / 256-bit) vector variants (mctq_set_tuning key 5)
+extern int g_multi_span;    // tiles per CTA of the multi-tensor LUT launch (mctq_set_tuning key 6)
 extern int g_pdl;           // programmatic dependent launch for the streaming kernels (mctq_set_tuning key 3)
 
 enum ChMode { CH_PT = 0, CH_VEC = 1, CH_ELEM = 2, CH_LAST = 3 };

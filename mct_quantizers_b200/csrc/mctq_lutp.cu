@@ -166,7 +166,7 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
 // the whole vector lies in one channel (CH_PT, CH_VEC with rows that are a multiple of 8): one 16-byte load, one 32-byte
 // store (STG.256), half the per-vector bookkeeping per element -- the 2-byte kernels are instruction-issue bound, not HBM bound.
 template <typename T, int CHMODE, int CODE, int UNROLL, int V>
-__global__ void __launch_bounds__(kThreads) fq_lutp_kernel(const LutPArgs a) {
+__device__ __forceinline__ void lutp_tile(const LutPArgs& a, const int64_t tile_index) {
     constexpr int WORDS_IN = V * sizeof(T) / 4;
     constexpr uint32_t TILE = kThreads * UNROLL * V;
     static_assert(V == 4 || (V == 8 && sizeof(T) == 2 && CHMODE != CH_ELEM), "vector width");
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(kThreads) fq_lutp_kernel(const LutPArgs a) {
     __shared__ __align__(8) uint64_t sm_bar;
 
     const uint32_t tid = threadIdx.x;
-    const int64_t t0 = (int64_t)blockIdx.x * TILE;
+    const int64_t t0 = tile_index * TILE;
     const int64_t remaining = a.n - t0;
     const bool full = remaining >= (int64_t)TILE;
     const T* xt = reinterpret_cast<const T*>(a.x) + t0;
@@ -356,22 +356,113 @@ __global__ void __launch_bounds__(kThreads) fq_lutp_kernel(const LutPArgs a) {
     }
 }
 
+template <typename T, int CHMODE, int CODE, int UNROLL, int V>
+__global__ void __launch_bounds__(kThreads) fq_lutp_kernel(const __grid_constant__ LutPArgs a) {
+    lutp_tile<T, CHMODE, CODE, UNROLL, V>(a, (int64_t)blockIdx.x);
+}
+
+// ---- many tensors, one launch (whole-model LUT weight quantization).  The per-tensor argument blocks and the first tile
+// of every tensor travel as KERNEL PARAMETERS (a __grid_constant__ struct of up to 32 KB): a CTA finds its tensor by a binary
+// search over the constant bank and reads that tensor's arguments from the constant bank with register-indexed LDC -- a
+// few tens of cycles, no global loads and no barrier before the data loads can be issued (a first version kept the table
+// in global memory: the dependent look-ups cost every CTA ~1000 cycles of idle residency and 15-20 % of the bandwidth).
+// No launch gaps and no per-launch tails between the tensors.
+constexpr int kMultiMaxDesc = 180;
+struct alignas(16) LutPMultiEntry {
+    LutPArgs a;
+    int32_t dtype, chmode, v, pad;
+};
+struct LutPMultiParams {
+    int32_t n_desc, span, pad[2];
+    int32_t starts[kMultiMaxDesc + 4];          // starts[k] = first span of tensor k; starts[n_desc] = number of spans
+    LutPMultiEntry e[kMultiMaxDesc];
+};
+static_assert(sizeof(LutPMultiParams) <= 32764, "kernel parameter space");
+
+// SPAN consecutive tiles of one tensor per CTA
+template <typename T, int CHMODE, int V, int SPAN>
+__device__ __forceinline__ void lutp_span(const LutPArgs& a, int64_t span) {
+    constexpr int64_t TILE = (int64_t)kThreads * 4 * V;
+    const int64_t first = span * SPAN;
+#pragma unroll 1
+    for (int g = 0; g < SPAN; ++g) {
+        if (g && (first + g) * TILE >= a.n) break;
+        if (g) __syncthreads();                  // everybody is done with the staged tables / the mbarrier of the previous tile
+        lutp_tile<T, CHMODE, MCTQ_CODES_NONE, 4, V>(a, first + g);
+    }
+}
+
+template <typename T, int SPAN>
+__device__ __forceinline__ void lutp_multi_dispatch(const LutPMultiEntry& e, int64_t span) {
+    constexpr int V8 = sizeof(T) == 2 ? 8 : 4;
+    if (e.chmode == CH_PT) {
+        if (e.v == 8) lutp_span<T, CH_PT, V8, SPAN>(e.a, span);
+        else lutp_span<T, CH_PT, 4, SPAN>(e.a, span);
+    } else if (e.chmode == CH_VEC) {
+        if (e.v == 8) lutp_span<T, CH_VEC, V8, SPAN>(e.a, span);
+        else lutp_span<T, CH_VEC, 4, SPAN>(e.a, span);
+    } else {
+        lutp_span<T, CH_ELEM, 4, SPAN>(e.a, span);
+    }
+}
+
+template <int SPAN>
+__global__ void __launch_bounds__(kThreads, (SPAN > 1 ? 4 : 1)) fq_lutp_multi_kernel(const __grid_constant__ LutPMultiParams p) {
+    const int tile = blockIdx.x;
+    int lo = 0, hi = p.n_desc;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (p.starts[mid] <= tile) lo = mid; else hi = mid;
+    }
+    const LutPMultiEntry& e = p.e[lo];
+    const int64_t t = (int64_t)(tile - p.starts[lo]);
+    if (e.dtype == MCTQ_F32) lutp_multi_dispatch<float, SPAN>(e, t);
+    else if (e.dtype == MCTQ_BF16) lutp_multi_dispatch<__nv_bfloat16, SPAN>(e, t);
+    else lutp_multi_dispatch<__half, SPAN>(e, t);
+}
+
 }  // namespace mctq
 
 using namespace mctq;
 
 namespace {
 
+// variant selection shared by the single-tensor and the multi-tensor entry points
+void lutp_variant(const LutPArgs& a, size_t esz, int idx_mode, int* chmode, int* v) {
+    // 8-element vectors for 2-byte inputs: 16-byte aligned x, 32-byte aligned y, 8-byte aligned int8 indices, rows a multiple of 8
+    bool v8 = g_wide && esz == 2 && aligned16(a.x) && (!a.y || aligned32(a.y)) &&
+              (idx_mode != MCTQ_CODES_INT8 || (reinterpret_cast<uintptr_t>(a.idx) & 7u) == 0);
+    if (a.C == 1) *chmode = CH_PT;
+    else if (a.inner % 4 == 0 && a.elem_offset % 4 == 0) {
+        *chmode = CH_VEC;
+        v8 = v8 && a.inner % 8 == 0 && a.elem_offset % 8 == 0;
+    } else {
+        *chmode = CH_ELEM;
+        v8 = false;
+    }
+    *v = v8 ? 8 : 4;
+}
+
+// channel-window geometry and dynamic shared memory of one tensor for tiles of kThreads * 4 * v elements
+int lutp_finish_args(LutPArgs& a, int chmode, int v, size_t* smem_out) {
+    const uint32_t tile = kThreads * 4 * (uint32_t)v;
+    uint32_t W = 1;
+    if (chmode != CH_PT) { set_window(a, tile); W = a.W; }
+    const size_t smem = (size_t)W * a.rec_floats * 4 + (((size_t)a.NC + 1 + 15) & ~(size_t)15) + (((size_t)a.P + 15) & ~(size_t)15);
+    if (smem > 64 * 1024) return MCTQ_E_RANGE;            // caller falls back to the generic kernel
+    *smem_out = smem;
+    return 0;
+}
+
 template <typename T, int CHMODE, int CODE, int V>
 int launch_lutp_tiles(const LutPArgs& a_in, cudaStream_t st) {
     constexpr int UNROLL = 4;
     constexpr uint32_t TILE = kThreads * UNROLL * V;
     LutPArgs a = a_in;
-    uint32_t W = 1;
-    if (CHMODE != CH_PT) { set_window(a, TILE); W = a.W; }
-    size_t smem = (size_t)W * a.rec_floats * 4 + (((size_t)a.NC + 1 + 15) & ~(size_t)15) + (((size_t)a.P + 15) & ~(size_t)15);
-    if (smem > 64 * 1024) return MCTQ_E_RANGE;            // caller falls back to the generic kernel
-    int rc = ensure_smem(fq_lutp_kernel<T, CHMODE, CODE, UNROLL, V>, smem);
+    size_t smem = 0;
+    int rc = lutp_finish_args(a, CHMODE, V, &smem);
+    if (rc) return rc;
+    rc = ensure_smem(fq_lutp_kernel<T, CHMODE, CODE, UNROLL, V>, smem);
     if (rc) return rc;
     int64_t tiles = (a.n + TILE - 1) / TILE;
     if (tiles > 0x7fffffffLL) return MCTQ_E_BADARG;
@@ -389,19 +480,37 @@ int launch_lutp_code(const LutPArgs& a, int idx_mode, cudaStream_t st) {
 
 template <typename T>
 int launch_lutp_typed(const LutPArgs& a, int idx_mode, cudaStream_t st) {
-    // 8-element vectors for 2-byte inputs: 16-byte aligned x, 8-byte aligned int8 indices, rows a multiple of 8
-    bool v8 = g_wide && sizeof(T) == 2 && aligned16(a.x) && (!a.y || aligned32(a.y)) &&
-              (idx_mode != MCTQ_CODES_INT8 || (reinterpret_cast<uintptr_t>(a.idx) & 7u) == 0);
-    if (a.C == 1) {
-        if (sizeof(T) == 2 && v8) return launch_lutp_code<T, CH_PT, sizeof(T) == 2 ? 8 : 4>(a, idx_mode, st);
-        return launch_lutp_code<T, CH_PT, 4>(a, idx_mode, st);
-    }
-    if (a.inner % 4 == 0 && a.elem_offset % 4 == 0) {
-        v8 = v8 && a.inner % 8 == 0 && a.elem_offset % 8 == 0;
-        if (sizeof(T) == 2 && v8) return launch_lutp_code<T, CH_VEC, sizeof(T) == 2 ? 8 : 4>(a, idx_mode, st);
-        return launch_lutp_code<T, CH_VEC, 4>(a, idx_mode, st);
-    }
+    constexpr int V8 = sizeof(T) == 2 ? 8 : 4;
+    int chmode, v;
+    lutp_variant(a, sizeof(T), idx_mode, &chmode, &v);
+    if (chmode == CH_PT) return v == 8 ? launch_lutp_code<T, CH_PT, V8>(a, idx_mode, st) : launch_lutp_code<T, CH_PT, 4>(a, idx_mode, st);
+    if (chmode == CH_VEC) return v == 8 ? launch_lutp_code<T, CH_VEC, V8>(a, idx_mode, st) : launch_lutp_code<T, CH_VEC, 4>(a, idx_mode, st);
     return launch_lutp_code<T, CH_ELEM, 4>(a, idx_mode, st);
+}
+
+// argument block of one prepared-LUT tensor (validated); shared by mctq_fq_lut_prepared and the multi-tensor plan
+int lutp_make_args(const void* x, float* y, void* idx, int64_t n, int x_dtype, const void* prepared_dev, int K, int bw, int is_signed,
+                   int64_t C, int64_t inner, int64_t elem_offset, int idx_mode, LutPArgs* out) {
+    if (!x || !prepared_dev || n < 0 || C < 1 || inner < 1 || elem_offset < 0 || (!y && idx_mode == MCTQ_CODES_NONE)) return MCTQ_E_BADARG;
+    if (idx_mode != MCTQ_CODES_NONE && !idx) return MCTQ_E_BADARG;
+    if (x_dtype < 0 || x_dtype > 2) return MCTQ_E_DTYPE;
+    PrepGeom g;
+    int rc = prep_geometry(K, bw, is_signed, C, &g);
+    if (rc) return rc;
+    if (idx_mode == MCTQ_CODES_INT4 && g.P > 16) return MCTQ_E_RANGE;
+    const size_t esz = x_dtype == MCTQ_F32 ? 4 : 2;
+    bool vec_ok = (reinterpret_cast<uintptr_t>(x) % (4 * esz)) == 0 && (!y || aligned16(y));
+    if (idx_mode != MCTQ_CODES_NONE) vec_ok = vec_ok && (reinterpret_cast<uintptr_t>(idx) & 3u) == 0;
+    if (!aligned16(prepared_dev)) vec_ok = false;  // the tables are staged with 16-byte bulk copies
+    if (!vec_ok) return MCTQ_E_BADARG;             // caller uses the generic entry point for misaligned views
+    LutPArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x = x; a.y = y; a.idx = idx; a.n = n; a.blob = reinterpret_cast<const uint8_t*>(prepared_dev);
+    a.P = g.P; a.NC = g.NC; a.rec_floats = g.rec_floats;
+    a.off_cells = (int32_t)g.off_cells; a.off_orig = (int32_t)g.off_orig; a.off_rec = (int32_t)g.off_rec;
+    a.C = C; a.inner = C == 1 ? 1 : inner; a.elem_offset = C == 1 ? 0 : elem_offset;
+    *out = a;
+    return 0;
 }
 
 }  // namespace
@@ -484,31 +593,120 @@ int mctq_lut_prepare(const void* table_host, int K, const float* thr_dev, int64_
 int mctq_fq_lut_prepared(const void* x, float* y, void* idx, int64_t n, int x_dtype, const void* prepared_dev, int K,
                          int lut_values_bitwidth, int is_signed, int64_t C, int64_t inner, int64_t elem_offset,
                          int idx_mode, void* stream) {
-    if (!x || !prepared_dev || n < 0 || C < 1 || inner < 1 || elem_offset < 0 || (!y && idx_mode == MCTQ_CODES_NONE)) return MCTQ_E_BADARG;
-    if (idx_mode != MCTQ_CODES_NONE && !idx) return MCTQ_E_BADARG;
-    PrepGeom g;
-    int rc = prep_geometry(K, lut_values_bitwidth, is_signed, C, &g);
-    if (rc) return rc;
-    if (idx_mode == MCTQ_CODES_INT4 && g.P > 16) return MCTQ_E_RANGE;
-    if (n == 0) return 0;
-    const size_t esz = x_dtype == MCTQ_F32 ? 4 : 2;
-    bool vec_ok = (reinterpret_cast<uintptr_t>(x) % (4 * esz)) == 0 && (!y || aligned16(y));
-    if (idx_mode != MCTQ_CODES_NONE) vec_ok = vec_ok && (reinterpret_cast<uintptr_t>(idx) & 3u) == 0;
-    if (!aligned16(prepared_dev)) vec_ok = false;  // the tables are staged with 16-byte bulk copies
-    if (!vec_ok) return MCTQ_E_BADARG;             // caller uses the generic entry point for misaligned views
     LutPArgs a;
-    memset(&a, 0, sizeof(a));
-    a.x = x; a.y = y; a.idx = idx; a.n = n; a.blob = reinterpret_cast<const uint8_t*>(prepared_dev);
-    a.P = g.P; a.NC = g.NC; a.rec_floats = g.rec_floats;
-    a.off_cells = (int32_t)g.off_cells; a.off_orig = (int32_t)g.off_orig; a.off_rec = (int32_t)g.off_rec;
-    a.C = C; a.inner = C == 1 ? 1 : inner; a.elem_offset = C == 1 ? 0 : elem_offset;
+    int rc = lutp_make_args(x, y, idx, n, x_dtype, prepared_dev, K, lut_values_bitwidth, is_signed, C, inner, elem_offset, idx_mode, &a);
+    if (rc) return rc;
+    if (n == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     switch (x_dtype) {
         case MCTQ_F32: return launch_lutp_typed<float>(a, idx_mode, st);
         case MCTQ_BF16: return launch_lutp_typed<__nv_bfloat16>(a, idx_mode, st);
-        case MCTQ_F16: return launch_lutp_typed<__half>(a, idx_mode, st);
-        default: return MCTQ_E_DTYPE;
+        default: return launch_lutp_typed<__half>(a, idx_mode, st);
     }
+}
+
+// ---- multi-tensor plan: a host blob [header][LutPMultiParams x n_chunks]; every chunk is one launch of up to kMultiMaxDesc tensors
+}  // extern "C"
+
+namespace {
+constexpr uint32_t kMultiMagic = 0x4d514c4du;   // 'MQLM'
+struct LutPMultiHeader {     // 64 bytes
+    uint32_t magic;
+    int32_t n_desc, n_chunks, span;
+    int64_t total_spans;
+    uint64_t smem_bytes;
+    int32_t reserved[8];
+};
+static_assert(sizeof(LutPMultiHeader) == 64, "multi header layout");
+
+size_t multi_bytes(int n_desc) {
+    const int chunks = (n_desc + kMultiMaxDesc - 1) / kMultiMaxDesc;
+    return sizeof(LutPMultiHeader) + (size_t)chunks * sizeof(LutPMultiParams);
+}
+
+// validates every tensor; fills the chunks when `blob` is given; returns the total number of spans (or < 0)
+int64_t multi_compile(const MctqLutTensorDesc* descs, int n_desc, uint8_t* blob) {
+    if (!descs || n_desc < 1) return MCTQ_E_BADARG;
+    const int span = g_multi_span == 1 ? 1 : 4;          // measured on Llama-7B shapes: 4 tiles per CTA +5 % (f32) / +2 % (bf16) over 1
+    LutPMultiHeader* h = reinterpret_cast<LutPMultiHeader*>(blob);
+    LutPMultiParams* chunks = blob ? reinterpret_cast<LutPMultiParams*>(blob + sizeof(LutPMultiHeader)) : nullptr;
+    int64_t total = 0;
+    size_t smem_max = 0;
+    for (int k = 0; k < n_desc; ++k) {
+        const MctqLutTensorDesc& d = descs[k];
+        if (d.n < 1 || !d.y) return MCTQ_E_BADARG;         // empty tensors do not belong in a plan
+        LutPMultiEntry e;
+        memset(&e, 0, sizeof(e));
+        int rc = lutp_make_args(d.x, d.y, nullptr, d.n, d.dtype, d.prepared_dev, d.K, d.lut_values_bitwidth, d.is_signed, d.C, d.inner,
+                                0, MCTQ_CODES_NONE, &e.a);
+        if (rc) return rc;
+        lutp_variant(e.a, d.dtype == MCTQ_F32 ? 4 : 2, MCTQ_CODES_NONE, &e.chmode, &e.v);
+        size_t smem = 0;
+        rc = lutp_finish_args(e.a, e.chmode, e.v, &smem);
+        if (rc) return rc;
+        if (smem > smem_max) smem_max = smem;
+        e.dtype = d.dtype;
+        const int64_t per_span = (int64_t)kThreads * 4 * e.v * span;
+        const int64_t spans = (d.n + per_span - 1) / per_span;
+        if (spans > 0x3fffffffLL) return MCTQ_E_BADARG;
+        if (chunks) {
+            LutPMultiParams& c = chunks[k / kMultiMaxDesc];
+            const int j = k % kMultiMaxDesc;
+            if (j == 0) { c.n_desc = 0; c.span = span; c.starts[0] = 0; }
+            if ((int64_t)c.starts[j] + spans > 0x7fffffffLL) return MCTQ_E_BADARG;
+            c.e[j] = e;
+            c.starts[j + 1] = c.starts[j] + (int32_t)spans;
+            c.n_desc = j + 1;
+        }
+        total += spans;
+    }
+    if (h) {
+        h->magic = kMultiMagic;
+        h->n_desc = n_desc;
+        h->n_chunks = (n_desc + kMultiMaxDesc - 1) / kMultiMaxDesc;
+        h->span = span;
+        h->total_spans = total;
+        h->smem_bytes = smem_max;
+    }
+    return total;
+}
+}  // namespace
+
+extern "C" {
+
+size_t mctq_lut_multi_plan_bytes(const MctqLutTensorDesc* descs, int n_desc) {
+    if (multi_compile(descs, n_desc, nullptr) < 0) return 0;
+    return multi_bytes(n_desc);
+}
+
+int64_t mctq_lut_multi_plan(const MctqLutTensorDesc* descs, int n_desc, void* plan_host_out, size_t plan_bytes) {
+    int64_t t = multi_compile(descs, n_desc, nullptr);
+    if (t < 0) return t;
+    if (!plan_host_out || plan_bytes < multi_bytes(n_desc)) return MCTQ_E_BADARG;
+    memset(plan_host_out, 0, multi_bytes(n_desc));
+    return multi_compile(descs, n_desc, reinterpret_cast<uint8_t*>(plan_host_out));
+}
+
+int mctq_fq_lut_prepared_multi(const void* plan_host, void* stream) {
+    if (!plan_host) return MCTQ_E_BADARG;
+    const LutPMultiHeader* h = reinterpret_cast<const LutPMultiHeader*>(plan_host);
+    if (h->magic != kMultiMagic || h->n_desc < 1 || h->n_chunks < 1) return MCTQ_E_BADARG;
+    const LutPMultiParams* chunks = reinterpret_cast<const LutPMultiParams*>(reinterpret_cast<const uint8_t*>(plan_host) + sizeof(LutPMultiHeader));
+    const size_t smem = (size_t)h->smem_bytes;
+    for (int c = 0; c < h->n_chunks; ++c) {
+        const LutPMultiParams& p = chunks[c];
+        const unsigned grid = (unsigned)p.starts[p.n_desc];
+        int rc;
+        if (p.span == 1) {
+            if ((rc = ensure_smem(fq_lutp_multi_kernel<1>, smem))) return rc;
+            rc = launch_streaming(fq_lutp_multi_kernel<1>, grid, smem, (cudaStream_t)stream, p);
+        } else {
+            if ((rc = ensure_smem(fq_lutp_multi_kernel<4>, smem))) return rc;
+            rc = launch_streaming(fq_lutp_multi_kernel<4>, grid, smem, (cudaStream_t)stream, p);
+        }
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 }  // extern "C"

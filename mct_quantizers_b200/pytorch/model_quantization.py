@@ -3,17 +3,35 @@
 The reference re-quantizes each wrapped weight with its own kernel(s) on every forward
 (mct_quantizers/pytorch/quantize_wrapper.py:228-240): 53 launches (+ 106 host syncs) for MobileNetV2.  Here all
 affine weight quantizers of a model are gathered into one descriptor table and run as ONE kernel
-(mctq_fq_affine_multi); LUT quantizers and user-defined quantizers keep their own call."""
+(mctq_fq_affine_multi), all LUT weight quantizers as a second one (mctq_fq_lut_prepared_multi); user-defined quantizers
+and tensors outside the prepared paths keep their own call."""
 from typing import Dict, List
 
 import torch
 
-from mct_quantizers_b200.ops import MultiTensorPlan
+from mct_quantizers_b200.ops import MultiTensorPlan, LutMultiPlan
 
 
 def _is_affine_weight_quantizer(q) -> bool:
     from mct_quantizers_b200.pytorch.quantizers import WeightsSymmetricInferableQuantizer, WeightsUniformInferableQuantizer
     return isinstance(q, (WeightsSymmetricInferableQuantizer, WeightsUniformInferableQuantizer)) and not q._use_custom_impl
+
+
+def _lut_item(q, w):
+    """LutMultiPlan item of a LUT weight quantizer (WeightsLUTSymmetric / WeightsLUTPOT), or None."""
+    from mct_quantizers_b200.pytorch.quantizers import WeightsLUTSymmetricInferableQuantizer
+    from mct_quantizers_b200.pytorch.quantizer_utils import lut_search_table
+    if not isinstance(q, WeightsLUTSymmetricInferableQuantizer) or q._use_custom_impl or not w.is_cuda:
+        return None
+    if q.per_channel and q.input_rank is not None and q.input_rank != w.dim():
+        return None                                   # the per-layer call raises the reference's error
+    if q.__dict__.get('_search_table') is None:
+        q._search_table = lut_search_table(q._lut_values_np, q.lut_values_bitwidth, True)
+    thr, = q._on(w.device, q._threshold_torch)
+    thr = thr.reshape(-1)
+    item = (w.detach(), q._search_table, int(q._lut_values_torch.numel()), thr, bool(q.per_channel),
+            int(q.channel_axis) if q.per_channel else 0, float(q.eps))
+    return item if LutMultiPlan.accepts(item) else None
 
 
 def plan_for(weight_vars) -> "WeightPlan":
@@ -24,25 +42,35 @@ class WeightPlan:
     """Pre-built launch plan over (name, weight, quantizer) triples.  Keeps output buffers; run() refreshes them."""
 
     def __init__(self, weight_vars):
-        self.names, self.fused_idx, self.other = [], [], []
-        items = []
+        self.names, self.fused_idx, self.lut_idx, self.other = [], [], [], []
+        items, lut_items = [], []
         for k, (name, w, q) in enumerate(weight_vars):
             self.names.append(name)
-            if _is_affine_weight_quantizer(q) and w.is_cuda and w.dtype in (torch.float32, torch.bfloat16, torch.float16):
+            ok_dtype = w.is_cuda and w.dtype in (torch.float32, torch.bfloat16, torch.float16)
+            lut_item = _lut_item(q, w) if ok_dtype else None
+            if _is_affine_weight_quantizer(q) and ok_dtype:
                 w.requires_grad = False
                 scales, zps = q._on(w.device, q.scales, q.zero_points)
                 items.append((w.detach(), scales.flatten(), zps.flatten(), q.channel_axis if q.per_channel else None,
                               q.min_quantized_domain, q.max_quantized_domain))
                 self.fused_idx.append(k)
+            elif lut_item is not None:
+                w.requires_grad = False
+                lut_items.append(lut_item)
+                self.lut_idx.append(k)
             else:
                 self.other.append((k, w, q))
         self.plan = MultiTensorPlan(items) if items else None
+        self.lut_plan = LutMultiPlan(lut_items) if lut_items else None
         self.n = len(weight_vars)
 
     def run(self) -> List[torch.Tensor]:
         out = [None] * self.n
         if self.plan is not None:
             for k, y in zip(self.fused_idx, self.plan.run()):
+                out[k] = y
+        if self.lut_plan is not None:
+            for k, y in zip(self.lut_idx, self.lut_plan.run()):
                 out[k] = y
         for k, w, q in self.other:
             out[k] = q(w)

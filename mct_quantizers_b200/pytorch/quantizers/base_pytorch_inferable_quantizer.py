@@ -65,6 +65,7 @@ class BasePyTorchInferableQuantizer(BaseInferableQuantizer):
     def __getstate__(self):
         state = dict(self.__dict__)
         state['_per_device'] = {}           # device copies are derived data; do not pickle them
+        state.pop('_direct_cache', None)    # launch constants (device pointers) of the lean LUT path
         return state
 
     def __setstate__(self, state):

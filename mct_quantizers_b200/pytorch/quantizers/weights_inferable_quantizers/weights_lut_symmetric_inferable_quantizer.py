@@ -28,9 +28,17 @@ def lut_weights_call(q, inputs, export_fn):
         if q.__dict__.get('_search_table') is None:   # built lazily (native library loads on first use; absent in objects unpickled from the reference)
             q._search_table = lut_search_table(q._lut_values_np, q.lut_values_bitwidth, True)
         thr, = q._on(inputs.device, q._threshold_torch)
-        outputs = lut_quantizer(inputs, lut_values=q._lut_values_torch, signed=True, threshold=thr,
-                                lut_values_bitwidth=q.lut_values_bitwidth, eps=q.eps, per_channel=q.per_channel,
-                                channel_axis=q.channel_axis, input_rank=q.input_rank, _table=q._search_table)
+        if ops.direct_ok(inputs) and (not q.per_channel or q.input_rank is None or q.input_rank == inputs.dim()):
+            # lean path: launch constants cached per (shape, dtype, device); same kernel as the general path below
+            cache = q.__dict__.get('_direct_cache')
+            if cache is None:
+                cache = q.__dict__['_direct_cache'] = {}
+            outputs = ops.lut_weights_direct(inputs.detach(), q._search_table, int(q._lut_values_torch.numel()), thr.reshape(-1),
+                                             bool(q.per_channel), int(q.channel_axis) if q.per_channel else 0, float(q.eps), cache)
+        else:
+            outputs = lut_quantizer(inputs, lut_values=q._lut_values_torch, signed=True, threshold=thr,
+                                    lut_values_bitwidth=q.lut_values_bitwidth, eps=q.eps, per_channel=q.per_channel,
+                                    channel_axis=q.channel_axis, input_rank=q.input_rank, _table=q._search_table)
     if q.enable_reuse and q.quantizer_first_run:
         q.resue_outputs = outputs
         q.quantizer_first_run = False

@@ -550,6 +550,73 @@ def test_whole_model_single_launch(Q, lib):
         assert mod.quantize_weights_batched().keys() == {'weight'}
 
 
+def test_whole_model_lut_single_launch(Q, lib):
+    """WeightPlan / quantize_model_weights with LUT weight quantizers: all of them in ONE mctq_fq_lut_prepared_multi
+    launch (next to the one launch of the affine quantizers) == the per-layer calls, bit for bit.  Mixed table:
+    f32 / bf16 / f16 weights, rows that are multiples of 8 (wide vectors), multiples of 4, odd (straddling vectors),
+    per-tensor, ragged tile tails, different centroid lists and bit widths, a POT quantizer."""
+    import mct_quantizers_b200 as mctq
+    from mct_quantizers_b200.pytorch.model_quantization import WeightPlan
+    rng = np.random.default_rng(33)
+    lut16 = [float(v) for v in sorted(rng.choice(np.arange(-128, 128), size=16, replace=False))]
+    lut8 = [float(v) for v in sorted(rng.choice(np.arange(-32, 32), size=8, replace=False))]
+    specs = [((24, 520), torch.float32, lut16, 8, True), ((40, 64), torch.bfloat16, lut16, 8, True),
+             ((6, 8200), torch.float16, lut8, 6, True), ((33, 27), torch.float32, lut8, 6, True),
+             ((5, 4100), torch.bfloat16, lut16, 8, True), ((12, 3, 3, 3), torch.float32, lut16, 8, True),
+             ((17, 1001), torch.float16, lut16, 8, False), ((3, 100000), torch.bfloat16, lut16, 8, True)]
+    triples = []
+    for k, (shape, dt, lut, bw, per_channel) in enumerate(specs):
+        w = torch.from_numpy(rng.standard_normal(shape).astype(np.float32) * 0.05).to(dt).to(DEV)
+        if per_channel:
+            thr = [float(v) + 1e-3 for v in w.float().abs().flatten(1).amax(1)]
+            q = Q.WeightsLUTSymmetricInferableQuantizer(4, lut, thr, True, 0, len(shape), bw)
+        elif k % 2:
+            q = Q.WeightsLUTPOTInferableQuantizer(4, lut, [0.25], False, None, None, bw)
+        else:
+            q = Q.WeightsLUTSymmetricInferableQuantizer(4, lut, [0.21], False, None, None, bw)
+        triples.append((f"w{k}", w, q))
+    # one affine tensor and one tensor the plan must leave to its own call (channel axis mismatch -> per-layer error path is
+    # not exercised here; a user-defined callable quantizer is)
+    wa = torch.randn(16, 33, device=DEV)
+    triples.append(("affine", wa, Q.WeightsSymmetricInferableQuantizer(8, [float(v) for v in wa.abs().amax(1)], True, 0)))
+    plan = WeightPlan(triples)
+    assert plan.lut_plan is not None and plan.lut_plan.n_desc == len(specs) and plan.plan is not None and not plan.other
+    before = lib.mctq_launch_count()
+    outs = plan.run()
+    assert lib.mctq_launch_count() - before == 2            # one affine launch + one LUT launch
+    for (name, w, q), y in zip(triples, outs):
+        want = q(w.clone())
+        assert y.dtype == want.dtype and y.shape == want.shape and torch.equal(y, want), name
+    # run() again after changing a weight in place: outputs are refreshed, buffers reused
+    ptrs = [y.data_ptr() for y in outs]
+    triples[0][1].mul_(0.5)
+    outs2 = plan.run()
+    assert [y.data_ptr() for y in outs2] == ptrs
+    assert torch.equal(outs2[0], triples[0][2](triples[0][1].clone()))
+    # through the wrappers of a model
+    lin = torch.nn.Linear(64, 40).to(DEV)
+    thr = [float(v) + 1e-3 for v in lin.weight.detach().abs().amax(1)]
+    wr = mctq.PytorchQuantizationWrapper(lin, {'weight': Q.WeightsLUTSymmetricInferableQuantizer(4, lut16, thr, True, 0, 2)})
+    model = torch.nn.Sequential(wr).to(DEV)
+    fused = mctq.quantize_model_weights(model)
+    assert torch.equal(fused['0']['weight'], wr.get_quantized_weights()['weight'])
+
+
+def test_lut_multi_plan_rejects_what_it_cannot_run(Q, lib):
+    """Tensors outside the prepared path (lut_values_bitwidth > 10, misaligned views) stay on their own call."""
+    from mct_quantizers_b200.pytorch.model_quantization import WeightPlan
+    lut = [float(v) for v in range(-2000, 2000, 250)]
+    w = torch.randn(8, 256, device=DEV)
+    q_wide = Q.WeightsLUTSymmetricInferableQuantizer(4, lut, [1.0] * 8, True, 0, 2, 14)
+    base = torch.randn(8 * 256 + 1, device=DEV)
+    w_mis = base[1:].view(8, 256)                                       # 4-byte aligned only
+    q_ok = Q.WeightsLUTSymmetricInferableQuantizer(4, [float(v) for v in range(-128, 128, 16)], [1.0] * 8, True, 0, 2)
+    plan = WeightPlan([("wide", w, q_wide), ("misaligned", w_mis, q_ok), ("ok", w, q_ok)])
+    assert plan.lut_plan is not None and plan.lut_plan.n_desc == 1 and len(plan.other) == 2
+    outs = plan.run()
+    assert torch.equal(outs[0], q_wide(w.clone())) and torch.equal(outs[1], q_ok(w_mis.clone())) and torch.equal(outs[2], q_ok(w.clone()))
+
+
 @pytest.mark.parametrize("dtype", ["float32", "bfloat16", "float16"])
 def test_multi_tensor_kernel_vs_oracle(dtype, lib):
     """mctq_fq_affine_multi over a mixed descriptor table: rows that are / are not multiples of 4, ragged tails,

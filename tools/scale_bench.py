@@ -108,7 +108,18 @@ def main():
         total = sum(a * b for a, b in shapes) * (es + 4)
         report(f"C3 Llama-7B 96 linears WeightsLUTSymmetric 4-bit K=16 per-channel {str(dt).split('.')[-1]} (layer-sharded)", total, ms,
                {"layers_on_rank0": len(sharding.shard_layers([a * b for a, b in shapes], world)[0])})
-        del bufs, quant
+        # the same shard as ONE launch: WeightPlan gathers the rank's LUT weight quantizers into a LutMultiPlan
+        # (mctq_fq_lut_prepared_multi); every layer has its own weight tensor here, as in the real model
+        from mct_quantizers_b200.pytorch.model_quantization import WeightPlan
+        layer_w = [torch.empty(shapes[li], device=dev).normal_(0, 0.02, generator=g).to(dt) for li in mine]
+        wplan = WeightPlan([(f"layer{li}", w, quant[shapes[li]]) for li, w in zip(mine, layer_w)])
+        assert wplan.lut_plan is not None and not wplan.other
+        per_layer = quant[shapes[mine[0]]](layer_w[0])
+        assert torch.equal(wplan.run()[0], per_layer)
+        ms = timed(lambda i: wplan.run(), args.reps)
+        report(f"C3 Llama-7B 96 linears WeightsLUTSymmetric 4-bit K=16 per-channel {str(dt).split('.')[-1]} (layer-sharded, ONE launch per rank)",
+               total, ms, {"layers_on_rank0": len(sharding.shard_layers([a * b for a, b in shapes], world)[0])})
+        del bufs, quant, wplan, layer_w, per_layer
         torch.cuda.empty_cache()
 
     # ------------------------------------------------------------------ C4: ViT-B/16 activations, batch-sharded
