@@ -396,29 +396,40 @@ __global__ void __launch_bounds__(kThreads) dequant_affine_kernel(const void* co
 //           elements walk (rem, c) forward
 // (q - zp) -> float goes through the magic-number trick (integer add into the mantissa of 1.5 * 2^23, one FADD) instead of
 // a quarter-rate I2F: exact for |q - zp| < 2^22.
-template <int CODE, int MODE>
+// V: codes per vector.  4 (one 32-bit / 16-bit load, one 16-byte store) or 8 (64-bit / 32-bit load, ONE 32-byte store:
+// STG.256) when the whole vector lies in one channel -- half the loads, stores and channel look-ups per element.
+template <int CODE, int MODE, int V>
 __global__ void __launch_bounds__(kThreads) dequant_affine_vec_kernel(const void* codes, int is_signed, float* y, int64_t n,
                                                                       const float* __restrict__ scale, const int32_t* __restrict__ zp,
                                                                       uint32_t C, uint32_t inner, int64_t elem_offset,
                                                                       const FastDiv div_inner, const FastDiv div_C) {
-    constexpr int V = 4, UNROLL = 4;
+    constexpr int UNROLL = 4;
     constexpr int64_t TILE = (int64_t)kThreads * UNROLL * V;
+    constexpr int RAW = (CODE == MCTQ_CODES_INT8 && V == 8) ? 2 : 1;           // 32-bit words of codes per vector
+    static_assert(V == 4 || (V == 8 && MODE != 2), "vector width");
     const int64_t t0 = (int64_t)blockIdx.x * TILE;
     pdl_wait();
     pdl_launch_dependents();
-    uint32_t raw[UNROLL];
+    uint32_t raw[UNROLL][RAW];
+    const uint8_t* cb = reinterpret_cast<const uint8_t*>(codes);
 #pragma unroll
     for (int j = 0; j < UNROLL; ++j) {
         const int64_t e = t0 + (int64_t)(j * kThreads + threadIdx.x) * V;
-        raw[j] = 0;
+#pragma unroll
+        for (int r = 0; r < RAW; ++r) raw[j][r] = 0;
         if (e + V <= n) {
-            if (CODE == MCTQ_CODES_INT8) raw[j] = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(codes) + e));
-            else raw[j] = __ldg(reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(codes) + (e >> 1)));
+            if (CODE == MCTQ_CODES_INT8) {
+                if (V == 8) { const uint2 v = __ldg(reinterpret_cast<const uint2*>(cb + e)); raw[j][0] = v.x; raw[j][RAW - 1] = v.y; }
+                else raw[j][0] = __ldg(reinterpret_cast<const uint32_t*>(cb + e));
+            } else {
+                if (V == 8) raw[j][0] = __ldg(reinterpret_cast<const uint32_t*>(cb + (e >> 1)));
+                else raw[j][0] = __ldg(reinterpret_cast<const uint16_t*>(cb + (e >> 1)));
+            }
         } else {
             for (int k = 0; k < V && e + k < n; ++k) {
                 const int64_t i = e + k;
-                if (CODE == MCTQ_CODES_INT8) raw[j] |= (uint32_t)reinterpret_cast<const uint8_t*>(codes)[i] << (8 * k);
-                else raw[j] |= (uint32_t)((reinterpret_cast<const uint8_t*>(codes)[i >> 1] >> ((i & 1) * 4)) & 0xf) << (4 * k);
+                if (CODE == MCTQ_CODES_INT8) raw[j][(k >> 2) % RAW] |= (uint32_t)cb[i] << (8 * (k & 3));
+                else raw[j][0] |= (uint32_t)((cb[i >> 1] >> ((i & 1) * 4)) & 0xf) << (4 * k);
             }
         }
     }
@@ -447,18 +458,19 @@ __global__ void __launch_bounds__(kThreads) dequant_affine_vec_kernel(const void
             sv = __ldg(scale + c);
             zv = __ldg(zp + c);
         }
-        float out[V];
+        uint32_t out[V];
 #pragma unroll
         for (int k = 0; k < V; ++k) {
             int q;
             if (CODE == MCTQ_CODES_INT8) {
-                q = is_signed ? (int)(int8_t)(raw[j] >> (8 * k)) : (int)((raw[j] >> (8 * k)) & 0xffu);
+                const uint32_t word = raw[j][(k >> 2) % RAW];
+                q = is_signed ? (int)(int8_t)(word >> (8 * (k & 3))) : (int)((word >> (8 * (k & 3))) & 0xffu);
             } else {
-                const int nib = (int)((raw[j] >> (4 * k)) & 0xfu);
+                const int nib = (int)((raw[j][0] >> (4 * k)) & 0xfu);
                 q = is_signed ? ((nib ^ 8) - 8) : nib;
             }
             const float d = __fsub_rn(__int_as_float(0x4B400000 + (q - zv)), kMagic);        // (float)(q - zp), exact
-            out[k] = __fmul_rn(d, sv);
+            out[k] = __float_as_uint(__fmul_rn(d, sv));
             if (MODE == 2) {
                 if (++rem == inner) {
                     rem = 0;
@@ -468,9 +480,12 @@ __global__ void __launch_bounds__(kThreads) dequant_affine_vec_kernel(const void
                 }
             }
         }
-        if (e + V <= n) st_stream(reinterpret_cast<uint4*>(y + e), make_uint4(__float_as_uint(out[0]), __float_as_uint(out[1]),
-                                                                               __float_as_uint(out[2]), __float_as_uint(out[3])));
-        else for (int k = 0; k < V && e + k < n; ++k) y[e + k] = out[k];
+        if (e + V <= n) {
+            if (V == 8) st_stream256(y + e, out);
+            else st_stream(reinterpret_cast<uint4*>(y + e), make_uint4(out[0], out[1], out[2], out[3]));
+        } else {
+            for (int k = 0; k < V && e + k < n; ++k) y[e + k] = __uint_as_float(out[k]);
+        }
     }
 }
 
@@ -789,15 +804,25 @@ int mctq_dequant_affine(const void* codes, int code_mode, int is_signed, float* 
     if (code_mode != MCTQ_CODES_INT8 && code_mode != MCTQ_CODES_INT4) return MCTQ_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
     if (aligned16(y) && (reinterpret_cast<uintptr_t>(codes) & 3u) == 0 && C < (1LL << 32) && inner < (1LL << 32)) {
-        const int64_t tile = (int64_t)kThreads * 16;
+        const int mode = C == 1 ? 0 : ((inner % 4 == 0 && elem_offset % 4 == 0) ? 1 : 2);
+        // 8 codes per vector (32-byte aligned y, the vector inside one channel) only where it measured faster on the B200:
+        // per-channel int4 (5.63 -> 6.14 TB/s; the channel look-up per vector halves).  Per-tensor and int8 variants are
+        // at 6.3-6.4 TB/s with 4-code vectors and lose ~3 % with 8 (key 5 = 2 forces 8 everywhere for experiments).
+        const bool fits8 = mode != 2 && aligned32(y) && (code_mode != MCTQ_CODES_INT8 || (reinterpret_cast<uintptr_t>(codes) & 7u) == 0) &&
+                           (mode == 0 || (inner % 8 == 0 && elem_offset % 8 == 0));
+        const bool v8 = fits8 && ((g_wide && mode == 1 && code_mode == MCTQ_CODES_INT4) || g_wide == 2);
+        const int64_t tile = (int64_t)kThreads * 4 * (v8 ? 8 : 4);
         const int64_t tiles = (n + tile - 1) / tile;
         if (tiles > 0x7fffffffLL) return MCTQ_E_BADARG;
-        const int mode = C == 1 ? 0 : ((inner % 4 == 0 && elem_offset % 4 == 0) ? 1 : 2);
         const uint32_t C32 = (uint32_t)C, in32 = (uint32_t)(C == 1 ? 1 : inner);
         const FastDiv di = make_fastdiv(in32), dc = make_fastdiv(C32);
-#define MCTQ_DQ(CM, MD) launch_streaming(dequant_affine_vec_kernel<CM, MD>, (unsigned)tiles, 0, st, codes, is_signed, y, n, scale, zp, C32, in32, elem_offset, di, dc)
-        if (code_mode == MCTQ_CODES_INT8) return mode == 0 ? MCTQ_DQ(MCTQ_CODES_INT8, 0) : mode == 1 ? MCTQ_DQ(MCTQ_CODES_INT8, 1) : MCTQ_DQ(MCTQ_CODES_INT8, 2);
-        return mode == 0 ? MCTQ_DQ(MCTQ_CODES_INT4, 0) : mode == 1 ? MCTQ_DQ(MCTQ_CODES_INT4, 1) : MCTQ_DQ(MCTQ_CODES_INT4, 2);
+#define MCTQ_DQ(CM, MD, VV) launch_streaming(dequant_affine_vec_kernel<CM, MD, VV>, (unsigned)tiles, 0, st, codes, is_signed, y, n, scale, zp, C32, in32, elem_offset, di, dc)
+        if (code_mode == MCTQ_CODES_INT8) {
+            if (v8) return mode == 0 ? MCTQ_DQ(MCTQ_CODES_INT8, 0, 8) : MCTQ_DQ(MCTQ_CODES_INT8, 1, 8);
+            return mode == 0 ? MCTQ_DQ(MCTQ_CODES_INT8, 0, 4) : mode == 1 ? MCTQ_DQ(MCTQ_CODES_INT8, 1, 4) : MCTQ_DQ(MCTQ_CODES_INT8, 2, 4);
+        }
+        if (v8) return mode == 0 ? MCTQ_DQ(MCTQ_CODES_INT4, 0, 8) : MCTQ_DQ(MCTQ_CODES_INT4, 1, 8);
+        return mode == 0 ? MCTQ_DQ(MCTQ_CODES_INT4, 0, 4) : mode == 1 ? MCTQ_DQ(MCTQ_CODES_INT4, 1, 4) : MCTQ_DQ(MCTQ_CODES_INT4, 2, 4);
 #undef MCTQ_DQ
     }
     int64_t blocks = (n + kThreads - 1) / kThreads;

@@ -34,7 +34,7 @@ int mctq_set_tuning(int key, int value) {
         case 2: prev = g_force_ieee_div; g_force_ieee_div = value ? 1 : 0; return prev;
         case 3: prev = g_pdl; g_pdl = value ? 1 : 0; return prev;
         case 4: prev = g_lut_shfl; g_lut_shfl = value ? 1 : 0; return prev;
-        case 5: prev = g_wide; g_wide = value ? 1 : 0; return prev;
+        case 5: prev = g_wide; if (value < 0 || value > 2) return MCTQ_E_BADARG; g_wide = value; return prev;
         case 6: prev = g_multi_span; if (value != 1 && value != 4) return MCTQ_E_BADARG; g_multi_span = value; return prev;
         default: return MCTQ_E_BADARG;
     }
