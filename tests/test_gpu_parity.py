@@ -348,6 +348,70 @@ def test_dequant_roundtrip(lib):
         assert torch.equal(codes, codes2)
 
 
+@pytest.mark.parametrize("wide", [0, 1, 2])
+def test_dequant_vector_variants(wide, lib):
+    """The streaming dequant kernel in every (code mode, channel mode, vector width) combination, ragged sizes included:
+    per-tensor, rows that are multiples of 8 / 4, odd rows; 4-code vectors (key 5 = 0), the default mix (1) and 8-code
+    vectors with 256-bit stores everywhere (2).  codes -> dequant == fake-quant values bit for bit."""
+    rng = np.random.default_rng(77 + wide)
+    prev = lib.mctq_set_tuning(5, wide)
+    try:
+        for (C, inner, outer, tail) in ((1, 1, 70001, 0), (13, 64, 37, 0), (7, 12, 211, 0), (5, 9, 333, 0), (3, 4096, 3, 0), (6, 8, 1000, 5)):
+            n_full = C * inner * outer
+            n = n_full - tail                                     # a flat prefix (ragged last vector)
+            x = _rand_x(rng, n, "float32", 1.0).to(DEV)
+            for bits, signed, mode in ((8, True, 1), (8, False, 1), (4, True, 2), (4, False, 2)):
+                qmin, qmax = (-(2 ** (bits - 1)), 2 ** (bits - 1) - 1) if signed else (0, 2 ** bits - 1)
+                scale = torch.from_numpy((np.abs(rng.standard_normal(C)) * 0.1 + 0.01).astype(np.float32)).to(DEV)
+                zp = torch.from_numpy((np.zeros(C) if signed else rng.integers(0, qmax + 1, size=C)).astype(np.int32)).to(DEV)
+                y = torch.empty_like(x)
+                codes = torch.empty(n if mode == 1 else (n + 1) // 2, dtype=torch.uint8, device=DEV)
+                assert lib.mctq_fq_affine(_vp(x), _vp(y), _vp(codes), n, 0, _vp(scale), _vp(zp), C, inner, 0, qmin, qmax, mode, _stream()) == 0
+                back = torch.full((n + 16,), 7.0, device=DEV)
+                assert lib.mctq_dequant_affine(_vp(codes), mode, int(signed), _vp(back), n, _vp(scale), _vp(zp), C, inner, 0, _stream()) == 0
+                assert torch.equal(back[:n].view(torch.int32), y.view(torch.int32)), (wide, C, inner, bits, signed)
+                assert (back[n:] == 7.0).all()
+    finally:
+        lib.mctq_set_tuning(5, prev)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_prepared_lut_wide_vectors_match_narrow(dtype, Q, lib):
+    """2-byte inputs: the 8-element / 256-bit-store variant of the prepared LUT kernel == the 4-element variant == the
+    oracle, values and indices (int8, packed int4), ragged tails, per-channel and per-tensor."""
+    rng = np.random.default_rng(5)
+    lut = [float(v) for v in sorted(rng.choice(np.arange(-128, 128), size=16, replace=False))]
+    for shape, per_channel in (((37, 264), True), ((3, 8200), True), ((70003,), False)):
+        x = torch.from_numpy((rng.standard_normal(shape) * 0.03).astype(np.float32)).to(dtype).to(DEV)
+        if per_channel:
+            thr = [float(v) + 1e-3 for v in x.float().abs().amax(1)]
+            q = Q.WeightsLUTSymmetricInferableQuantizer(4, lut, thr, True, 0, 2)
+        else:
+            thr = [0.11]
+            q = Q.WeightsLUTSymmetricInferableQuantizer(4, lut, thr, False)
+        from mct_quantizers_b200.pytorch.quantizer_utils import lut_search_table
+        table = lut_search_table(np.asarray(lut, np.float32), 8, True)
+        thr_t = torch.tensor(thr, dtype=torch.float32, device=DEV)
+        outs = []
+        for wide in (0, 1):
+            prev = lib.mctq_set_tuning(5, wide)
+            try:
+                y = q(x.clone())
+                i8 = torch.ops.mctq.lut_indices(x, table, 16, thr_t, per_channel, 0, 1e-8, 1)
+                i4 = torch.ops.mctq.lut_indices(x, table, 16, thr_t, per_channel, 0, 1e-8, 2)
+                torch.cuda.synchronize()
+            finally:
+                lib.mctq_set_tuning(5, prev)
+            outs.append((y, i8, i4))
+        for a, b in zip(outs[0], outs[1]):
+            assert torch.equal(a, b)
+        xb = x.cpu().contiguous().view(torch.int16).numpy().view(np.uint16)
+        C, inner = (shape[0], shape[1]) if per_channel else (1, 1)
+        want = oracle.fq_lut(xb, oracle.BF16 if dtype == torch.bfloat16 else oracle.F16, np.asarray(lut, np.float32),
+                             np.asarray(thr, np.float64).astype(np.float32), C, inner, 8, True, 1e-8)
+        assert np.array_equal(outs[1][0].cpu().numpy().view(np.uint32), np.asarray(want).reshape(shape).view(np.uint32))
+
+
 def test_bad_arguments(lib):
     x = torch.zeros(16, device=DEV)
     y = torch.empty_like(x)
