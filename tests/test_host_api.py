@@ -284,6 +284,45 @@ def test_multi_plan_host_helper():
     assert total == 6 and list(starts) == [0, 1, 2, 6]
 
 
+def test_lut_multi_plan_host_compiler():
+    """mctq_lut_multi_plan is host-only code: descriptor validation, variant selection per tensor, span counts and the
+    180-tensors-per-launch chunking can be checked without a GPU (device pointers are never dereferenced here)."""
+    lib = _native.load()
+    assert ctypes.sizeof(_native.MctqLutTensorDesc) == 64
+
+    def desc(n, C, inner, dtype=0, x=0x7f0000000000, y=0x7f1000000000, blob=0x7f2000000000, K=16, bw=8):
+        d = _native.MctqLutTensorDesc()
+        d.x, d.y, d.prepared_dev, d.n, d.C, d.inner = x, y, blob, n, C, inner
+        d.dtype, d.K, d.lut_values_bitwidth, d.is_signed = dtype, K, bw, 1
+        return d
+
+    def plan(ds):
+        arr = (_native.MctqLutTensorDesc * len(ds))(*ds)
+        nb = lib.mctq_lut_multi_plan_bytes(ctypes.cast(arr, ctypes.c_void_p), len(ds))
+        if nb == 0:
+            return 0, lib.mctq_lut_multi_plan(ctypes.cast(arr, ctypes.c_void_p), len(ds), None, 0), None
+        buf = (ctypes.c_uint8 * nb)()
+        return nb, lib.mctq_lut_multi_plan(ctypes.cast(arr, ctypes.c_void_p), len(ds), ctypes.cast(buf, ctypes.c_void_p), nb), buf
+
+    span_f32 = 256 * 4 * 4 * 4            # threads x unroll x 4-element vectors x 4 tiles per CTA
+    span_bf16_wide = 256 * 4 * 8 * 4      # 2-byte inputs, rows a multiple of 8: 8-element vectors
+    nb, total, buf = plan([desc(span_f32 * 3 + 1, 128, 4096), desc(5, 1, 1), desc(span_bf16_wide * 2, 64, 4096, dtype=1),
+                           desc(span_f32 + 1, 64, 36, dtype=1)])       # rows of 36: not a multiple of 8 -> 4-element vectors
+    assert total == 4 + 1 + 2 + 2 and nb > 64
+    hdr = np.frombuffer(bytes(buf)[:32], dtype=np.int32)
+    assert hdr[1] == 4 and hdr[2] == 1 and hdr[3] == 4                 # n_desc, one launch, 4 tiles per CTA
+    # more than 180 tensors: several launches, every one with its own tile numbering
+    nb2, total2, buf2 = plan([desc(1000 + k, 8, 128) for k in range(400)])
+    assert total2 == 400 and np.frombuffer(bytes(buf2)[:32], dtype=np.int32)[2] == 3
+    assert nb2 > 2 * nb
+    # tensors the prepared path cannot run are refused (the caller keeps them on their own call)
+    assert plan([desc(100, 4, 25, x=0x7f0000000004)])[1] == -1         # misaligned x
+    assert plan([desc(100, 4, 25, bw=14)])[1] == -3                    # lut_values_bitwidth > 10: cell table too large
+    assert plan([desc(0, 1, 1)])[1] == -1                              # empty tensor
+    assert plan([desc(100, 1, 1, dtype=5)])[1] == -2
+    assert lib.mctq_fq_lut_prepared_multi(None, None) == -1
+
+
 @pytest.mark.skipif(HAS_GPU, reason="checks the no-GPU failure mode")
 def test_fails_loudly_without_a_gpu():
     """No CPU arithmetic path: a call on a machine without CUDA raises instead of silently computing elsewhere."""
