@@ -407,9 +407,14 @@ def test_prepared_lut_wide_vectors_match_narrow(dtype, Q, lib):
             assert torch.equal(a, b)
         xb = x.cpu().contiguous().view(torch.int16).numpy().view(np.uint16)
         C, inner = (shape[0], shape[1]) if per_channel else (1, 1)
-        want = oracle.fq_lut(xb, oracle.BF16 if dtype == torch.bfloat16 else oracle.F16, np.asarray(lut, np.float32),
-                             np.asarray(thr, np.float64).astype(np.float32), C, inner, 8, True, 1e-8)
+        want, want_idx = oracle.fq_lut(xb, oracle.BF16 if dtype == torch.bfloat16 else oracle.F16, np.asarray(lut, np.float32),
+                                       np.asarray(thr, np.float64).astype(np.float32), C, inner, 8, True, 1e-8, want_idx=True)
         assert np.array_equal(outs[1][0].cpu().numpy().view(np.uint32), np.asarray(want).reshape(shape).view(np.uint32))
+        # sorted centroid list: the kernel emits the sorted position directly (identity permutation flag in the blob)
+        assert np.array_equal(outs[1][1].cpu().numpy().reshape(-1).astype(np.int32), np.asarray(want_idx).reshape(-1))
+        i4 = outs[1][2].cpu().numpy()
+        un = np.stack([i4 & 0xF, i4 >> 4], 1).reshape(-1)[:x.numel()].astype(np.int32)
+        assert np.array_equal(un, np.asarray(want_idx).reshape(-1))
 
 
 def test_bad_arguments(lib):
@@ -664,6 +669,36 @@ def test_whole_model_lut_single_launch(Q, lib):
     model = torch.nn.Sequential(wr).to(DEV)
     fused = mctq.quantize_model_weights(model)
     assert torch.equal(fused['0']['weight'], wr.get_quantized_weights()['weight'])
+
+
+def test_weight_plan_under_cuda_graph(Q, lib):
+    """WeightPlan.run() (one affine + one LUT multi-tensor launch; the LUT plan travels as 27 KB of kernel parameters) can be
+    captured in a CUDA graph; a replay re-quantizes the CURRENT contents of the weights into the same output buffers."""
+    from mct_quantizers_b200.pytorch.model_quantization import WeightPlan
+    rng = np.random.default_rng(8)
+    lut = [float(v) for v in sorted(rng.choice(np.arange(-128, 128), size=16, replace=False))]
+    w1 = torch.randn(48, 256, device=DEV) * 0.05
+    w2 = (torch.randn(16, 3, 3, 3, device=DEV) * 0.05).bfloat16()
+    w3 = torch.randn(32, 72, device=DEV)
+    q1 = Q.WeightsLUTSymmetricInferableQuantizer(4, lut, [float(v) + 1e-3 for v in w1.abs().amax(1)], True, 0, 2)
+    q2 = Q.WeightsLUTSymmetricInferableQuantizer(4, lut, [0.2] * 16, True, 0, 4)
+    q3 = Q.WeightsSymmetricInferableQuantizer(8, [float(v) for v in w3.abs().amax(1)], True, 0)
+    plan = WeightPlan([("a", w1, q1), ("b", w2, q2), ("c", w3, q3)])
+    plan.run()                                               # warm-up outside the capture (shared-memory attributes, caches)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            outs = plan.run()
+    torch.cuda.current_stream().wait_stream(side)
+    for w in (w1, w2, w3):
+        w.mul_(0.7)                                          # new weight values, same storage
+    graph.replay()
+    torch.cuda.synchronize()
+    for (w, q), y in zip(((w1, q1), (w2, q2), (w3, q3)), outs):
+        assert torch.equal(y, q(w.clone()))
 
 
 def test_lut_multi_plan_rejects_what_it_cannot_run(Q, lib):
