@@ -444,7 +444,13 @@ def _table_on(table, device):
     key = (table.data_ptr(), str(device))
     hit = _LUT_DEV_TABLES.get(key)
     if hit is None:
-        hit = (table, table.to(device))
+        if torch.cuda.is_current_stream_capturing():
+            # first use inside a CUDA-graph capture: the upload becomes a node of the graph and must read pinned memory
+            # that outlives the graph (kept in the cache entry)
+            src = table.pin_memory()
+            hit = (table, src.to(device, non_blocking=True), src)
+        else:
+            hit = (table, table.to(device))
         _LUT_DEV_TABLES[key] = hit
     return hit[1]
 
@@ -462,6 +468,8 @@ def _prepared_for(table, K, device, thr_dev, eps, scalar, divisor, thr_f32, roun
         C = thr_dev.numel()
     hit = _LUT_PREPARED.get(key)
     if hit is None:
+        if torch.cuda.is_current_stream_capturing():
+            return None                     # preparation synchronises: not inside a CUDA-graph capture (generic kernel instead)
         lib = _native.load()
         bw, signed = _table_header(table)
         nbytes = lib.mctq_lut_prepared_bytes(int(K), bw, signed, C)
@@ -473,6 +481,7 @@ def _prepared_for(table, K, device, thr_dev, eps, scalar, divisor, thr_f32, roun
                                           float(np.float32(eps)), int(scalar), float(np.float32(divisor)),
                                           float(np.float32(thr_f32)), int(round_dtype), _ptr(blob), nbytes, _stream(device))
             _native.check(rc, "mctq_lut_prepare")
+            torch.cuda.current_stream(device).synchronize()      # one-off: the blob may be used from any stream afterwards
         hit = ((table, thr_dev), blob, bw, signed)
         _LUT_PREPARED[key] = hit
     return hit
@@ -552,7 +561,8 @@ def lut_weights_direct(x, table, K, threshold, per_channel, axis, eps, cache):
                     hit = (tag, int(K), prep[2], prep[3], C, inner, prep[1].data_ptr(), (thr, prep), x.device.index)
             if len(cache) > 16:
                 cache.clear()
-            cache[key] = hit
+            if hit or not torch.cuda.is_current_stream_capturing():     # a capture only postpones the preparation
+                cache[key] = hit
         if hit:
             tag, K_, bw, signed, C, inner, blob_ptr, _, index = hit
             if (x.data_ptr() & 15) == 0:

@@ -701,6 +701,30 @@ def test_weight_plan_under_cuda_graph(Q, lib):
         assert torch.equal(y, q(w.clone()))
 
 
+def test_first_lut_call_inside_a_graph_capture(Q):
+    """A LUT quantizer whose FIRST call happens while a CUDA graph is being captured: the one-off table preparation
+    (which synchronises) is postponed, the generic kernel is captured instead; replays and later eager calls agree."""
+    rng = np.random.default_rng(9)
+    lut = [float(v) for v in rng.choice(np.arange(-128, 128), size=16, replace=False)]
+    w = torch.randn(24, 136, device=DEV) * 0.05
+    x = torch.randn(4, 3000, device=DEV).half()
+    qw = Q.WeightsLUTSymmetricInferableQuantizer(4, lut, [float(v) + 1e-3 for v in w.abs().amax(1)], True, 0, 2)
+    qa = Q.ActivationLutPOTInferableQuantizer(4, lut, [2.0], True)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            yw, ya = qw(w), qa(x)
+    torch.cuda.current_stream().wait_stream(side)
+    w.mul_(0.9)
+    x.mul_(1.1)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(yw, qw(w.clone())) and torch.equal(ya, qa(x.clone()))      # eager calls: prepared kernels
+
+
 def test_lut_multi_plan_rejects_what_it_cannot_run(Q, lib):
     """Tensors outside the prepared path (lut_values_bitwidth > 10, misaligned views) stay on their own call."""
     from mct_quantizers_b200.pytorch.model_quantization import WeightPlan
