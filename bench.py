@@ -244,7 +244,7 @@ def run_b200(args):
     logging.getLogger("MCT Quantizers B200").setLevel(logging.ERROR)     # 53 identical "range adjusted" notices
     from mct_quantizers_b200.pytorch import quantizers as Q
     from mct_quantizers_b200.pytorch.model_quantization import WeightPlan
-    lib = _native.load(build_if_missing=False)
+    lib = _native.load()
 
     # ---- synthetic model state, generated on the device (seeded per rank)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)

@@ -27,7 +27,7 @@ def Q():
 @pytest.fixture(scope="module")
 def lib():
     from mct_quantizers_b200 import _native
-    return _native.load(build_if_missing=False)
+    return _native.load()
 
 
 def _vp(t):

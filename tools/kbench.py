@@ -51,7 +51,7 @@ def main():
     ap.add_argument("--json", default=None)
     ap.add_argument("--tune", default="", help="comma separated key=value pairs for mctq_set_tuning (experiments)")
     args = ap.parse_args()
-    lib = _native.load(build_if_missing=False)
+    lib = _native.load()
     for kv in filter(None, args.tune.split(",")):
         k, v = kv.split("=")
         assert lib.mctq_set_tuning(int(k), int(v)) >= 0

@@ -33,7 +33,7 @@ def main():
     ap.add_argument("--mb", type=float, default=512.0)
     ap.add_argument("--order", default="gpurun_out/variants_order.json")
     args = ap.parse_args()
-    lib = _native.load(build_if_missing=False)
+    lib = _native.load()
     dev = torch.device("cuda:0")
     st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)  # noqa: E731
     rng = np.random.default_rng(0)
