@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(kThreads) dequant_affine_vec_kernel(const void
 }
 
 // ------------------------------------------------------------------------------------------ multi-tensor
-constexpr int kMultiTile = 2048;   // elements per tile, any dtype
+constexpr int kMultiTile = 2048;   // elements per tile, any dtype (8192 measured: ResNet-18 29 -> 29 us, MobileNetV2 10 -> 17 us)
 
 // channel of logical element i: 32-bit arithmetic whenever the tensor has fewer than 2^32 elements
 __device__ __forceinline__ int64_t multi_channel(int64_t i, const MctqTensorDesc& d, bool small) {

@@ -388,11 +388,15 @@ struct alignas(16) LutPMultiEntry {
     LutPArgs a;
     int32_t dtype, chmode, v, pad;
 };
-struct LutPMultiParams {
+// The parameter block is copied by every launch (~20 us for 27 KB), so its capacity is a template parameter: 16 / 64 / 180
+// tensors (2.4 / 9.5 / 26.7 KB); the host plan keeps full-capacity chunks and the launch copies what is used.
+template <int CAP>
+struct LutPMultiParamsT {
     int32_t n_desc, span, pad[2];
-    int32_t starts[kMultiMaxDesc + 4];          // starts[k] = first span of tensor k; starts[n_desc] = number of spans
-    LutPMultiEntry e[kMultiMaxDesc];
+    int32_t starts[CAP + 4];                    // starts[k] = first span of tensor k; starts[n_desc] = number of spans
+    LutPMultiEntry e[CAP];
 };
+using LutPMultiParams = LutPMultiParamsT<kMultiMaxDesc>;
 static_assert(sizeof(LutPMultiParams) <= 32764, "kernel parameter space");
 
 // SPAN consecutive tiles of one tensor per CTA
@@ -422,8 +426,8 @@ __device__ __forceinline__ void lutp_multi_dispatch(const LutPMultiEntry& e, int
     }
 }
 
-template <int SPAN>
-__global__ void __launch_bounds__(kThreads, (SPAN > 1 ? 4 : 1)) fq_lutp_multi_kernel(const __grid_constant__ LutPMultiParams p) {
+template <int SPAN, int CAP>
+__global__ void __launch_bounds__(kThreads, (SPAN > 1 ? 4 : 1)) fq_lutp_multi_kernel(const __grid_constant__ LutPMultiParamsT<CAP> p) {
     const int tile = blockIdx.x;
     int lo = 0, hi = p.n_desc;
     while (hi - lo > 1) {
@@ -637,6 +641,18 @@ struct LutPMultiHeader {     // 64 bytes
 };
 static_assert(sizeof(LutPMultiHeader) == 64, "multi header layout");
 
+template <int SPAN, int CAP>
+int launch_multi_chunk(const LutPMultiParams& c, size_t smem, cudaStream_t st) {
+    static thread_local LutPMultiParamsT<CAP> p;             // up to 27 KB: not on the stack
+    p.n_desc = c.n_desc;
+    p.span = c.span;
+    memcpy(p.starts, c.starts, ((size_t)c.n_desc + 1) * sizeof(int32_t));
+    memcpy(p.e, c.e, (size_t)c.n_desc * sizeof(LutPMultiEntry));
+    int rc = ensure_smem(fq_lutp_multi_kernel<SPAN, CAP>, smem);
+    if (rc) return rc;
+    return launch_streaming(fq_lutp_multi_kernel<SPAN, CAP>, (unsigned)c.starts[c.n_desc], smem, st, p);
+}
+
 size_t multi_bytes(int n_desc) {
     const int chunks = (n_desc + kMultiMaxDesc - 1) / kMultiMaxDesc;
     return sizeof(LutPMultiHeader) + (size_t)chunks * sizeof(LutPMultiParams);
@@ -713,15 +729,10 @@ int mctq_fq_lut_prepared_multi(const void* plan_host, void* stream) {
     const size_t smem = (size_t)h->smem_bytes;
     for (int c = 0; c < h->n_chunks; ++c) {
         const LutPMultiParams& p = chunks[c];
-        const unsigned grid = (unsigned)p.starts[p.n_desc];
         int rc;
-        if (p.span == 1) {
-            if ((rc = ensure_smem(fq_lutp_multi_kernel<1>, smem))) return rc;
-            rc = launch_streaming(fq_lutp_multi_kernel<1>, grid, smem, (cudaStream_t)stream, p);
-        } else {
-            if ((rc = ensure_smem(fq_lutp_multi_kernel<4>, smem))) return rc;
-            rc = launch_streaming(fq_lutp_multi_kernel<4>, grid, smem, (cudaStream_t)stream, p);
-        }
+        if (p.n_desc <= 16) rc = p.span == 1 ? launch_multi_chunk<1, 16>(p, smem, (cudaStream_t)stream) : launch_multi_chunk<4, 16>(p, smem, (cudaStream_t)stream);
+        else if (p.n_desc <= 64) rc = p.span == 1 ? launch_multi_chunk<1, 64>(p, smem, (cudaStream_t)stream) : launch_multi_chunk<4, 64>(p, smem, (cudaStream_t)stream);
+        else rc = p.span == 1 ? launch_multi_chunk<1, kMultiMaxDesc>(p, smem, (cudaStream_t)stream) : launch_multi_chunk<4, kMultiMaxDesc>(p, smem, (cudaStream_t)stream);
         if (rc) return rc;
     }
     return 0;

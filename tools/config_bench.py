@@ -110,6 +110,20 @@ def main():
     plan = WeightPlan([tv for w in wrappers for tv in w.get_weights_vars()])
     ms = time_gpu(lambda i: plan.run())
     rec("C1", "ResNet-18 20 conv weights, one multi-tensor launch (WeightPlan.run)", ms, n_w * 8)
+    # the same 20 tensors with 4-bit LUT quantizers: per-layer calls vs one multi-tensor LUT launch
+    import numpy as np
+    lut = [float(v) for v in sorted(np.random.default_rng(0).choice(np.arange(-128, 128), size=16, replace=False))]
+    lut_vars = []
+    for k, w in enumerate(wrappers):
+        wt = w.get_weights_vars()[0][1].detach()              # the float weight lives on the wrapper, not on the wrapped layer
+        thr = [float(v) + 1e-6 for v in wt.abs().flatten(1).amax(1)]
+        lut_vars.append((f"w{k}", wt, Q.WeightsLUTSymmetricInferableQuantizer(4, lut, thr, True, 0, 4)))
+    ms = time_gpu(lambda i: [q(wt) for _, wt, q in lut_vars])
+    rec("C1", "ResNet-18 20 conv weights, LUT 4-bit, per-layer calls (20 launches)", ms, n_w * 8)
+    lplan = WeightPlan(lut_vars)
+    assert lplan.lut_plan is not None and not lplan.other
+    ms = time_gpu(lambda i: lplan.run())
+    rec("C1", "ResNet-18 20 conv weights, LUT 4-bit, one multi-tensor launch (WeightPlan.run)", ms, n_w * 8)
     ms = time_gpu(lambda i: mctq.quantize_model_weights(model), reps=10)
     rec("C1", "ResNet-18 quantize_model_weights(model) incl. plan construction", ms, n_w * 8)
     holder = mctq.PytorchActivationQuantizationHolder(Q.ActivationPOTInferableQuantizer(8, [4.0], True)).to(DEV)
