@@ -458,6 +458,18 @@ __global__ void __launch_bounds__(kThreads) dequant_affine_vec_kernel(const void
             sv = __ldg(scale + c);
             zv = __ldg(zp + c);
         }
+        // MODE 2, rows of at least one vector: the vector crosses at most one row boundary, so the parameters of the next
+        // channel are fetched up front and selected per element (no divergent reloads inside the element loop)
+        const bool two_rows = MODE == 2 && inner >= (uint32_t)V;
+        uint32_t first_cnt = V;
+        float sv1 = sv;
+        int zv1 = zv;
+        if (two_rows) {
+            first_cnt = inner - rem;
+            const uint32_t c1 = (c + 1 == C) ? 0 : c + 1;
+            sv1 = __ldg(scale + c1);
+            zv1 = __ldg(zp + c1);
+        }
         uint32_t out[V];
 #pragma unroll
         for (int k = 0; k < V; ++k) {
@@ -469,9 +481,12 @@ __global__ void __launch_bounds__(kThreads) dequant_affine_vec_kernel(const void
                 const int nib = (int)((raw[j][0] >> (4 * k)) & 0xfu);
                 q = is_signed ? ((nib ^ 8) - 8) : nib;
             }
-            const float d = __fsub_rn(__int_as_float(0x4B400000 + (q - zv)), kMagic);        // (float)(q - zp), exact
-            out[k] = __float_as_uint(__fmul_rn(d, sv));
-            if (MODE == 2) {
+            float se = sv;
+            int ze = zv;
+            if (two_rows && (uint32_t)k >= first_cnt) { se = sv1; ze = zv1; }
+            const float d = __fsub_rn(__int_as_float(0x4B400000 + (q - ze)), kMagic);        // (float)(q - zp), exact
+            out[k] = __float_as_uint(__fmul_rn(d, se));
+            if (MODE == 2 && !two_rows) {
                 if (++rem == inner) {
                     rem = 0;
                     c = (c + 1 == C) ? 0 : c + 1;

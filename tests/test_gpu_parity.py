@@ -356,7 +356,8 @@ def test_dequant_vector_variants(wide, lib):
     rng = np.random.default_rng(77 + wide)
     prev = lib.mctq_set_tuning(5, wide)
     try:
-        for (C, inner, outer, tail) in ((1, 1, 70001, 0), (13, 64, 37, 0), (7, 12, 211, 0), (5, 9, 333, 0), (3, 4096, 3, 0), (6, 8, 1000, 5)):
+        for (C, inner, outer, tail) in ((1, 1, 70001, 0), (13, 64, 37, 0), (7, 12, 211, 0), (5, 9, 333, 0), (3, 4096, 3, 0), (6, 8, 1000, 5),
+                                     (11, 3, 500, 0), (4, 1, 1000, 0), (3, 5, 2001, 2), (9, 4097, 2, 0)):
             n_full = C * inner * outer
             n = n_full - tail                                     # a flat prefix (ragged last vector)
             x = _rand_x(rng, n, "float32", 1.0).to(DEV)
