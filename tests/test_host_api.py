@@ -331,6 +331,16 @@ def test_fails_loudly_without_a_gpu():
         q(torch.randn(8))
     with pytest.raises(_native.MctqError):
         Q.WeightsLUTSymmetricInferableQuantizer(2, [0.0, 1.0], [1.0], False)(torch.randn(8))
+    import mct_quantizers_b200 as mctq
+    with pytest.raises(_native.MctqError, match="no CUDA device"):
+        with mctq.host_pipeline():
+            pass
+    # whole-model plans never take host tensors into a launch: they stay on the per-layer call, which raises as above
+    from mct_quantizers_b200.pytorch.model_quantization import WeightPlan
+    plan = WeightPlan([("w", torch.randn(4, 8), Q.WeightsSymmetricInferableQuantizer(8, [1.0] * 4, True, 0))])
+    assert plan.plan is None and plan.lut_plan is None and len(plan.other) == 1
+    with pytest.raises(_native.MctqError):
+        plan.run()
 
 
 def test_product_never_imports_the_oracle():
