@@ -105,6 +105,17 @@ def main():
                     lambda xl=xl, yf=yf, n=n, tag=tag, thr=thr, C=C, inner=inner:
                     lib.mctq_fq_lut(vp(xl), vp(yf), None, n, tag, vp(table_dev), 16, vp(thr), C, inner, 0, 1e-8, 0, st()))
 
+    # whole-model LUT launch: three Llama-7B matrices (bf16) in ONE mctq_fq_lut_prepared_multi launch
+    from mct_quantizers_b200 import ops
+    items, total = [], 0
+    for shp in ((11008, 4096), (11008, 4096), (4096, 11008)):
+        w = torch.empty(shp, device=dev).normal_(0, 0.02).bfloat16()
+        thr = w.float().abs().amax(1).contiguous()
+        items.append((w, table_host, 16, thr, True, 0, 1e-8))
+        total += w.numel()
+    mplan = ops.LutMultiPlan(items)
+    jobs.append(("lut-prepared multi-tensor launch, 3 Llama-7B matrices (kernel-parameter plan) [bf16]", total * 6, lambda: (mplan.run(), 0)[1], total))
+
     torch.cuda.synchronize()
     for _, _, fn, _ in jobs:          # warm-up (module load, shared-memory attributes) outside the profiled range
         rc = fn()
