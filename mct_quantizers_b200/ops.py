@@ -905,10 +905,7 @@ class LutMultiPlan:
         if got is None:
             return False
         lib = _native.load()
-        d = got[0]
-        y_probe = torch.empty(0, dtype=torch.float32, device=x.device)      # alignment of fresh allocations is >= 256 bytes
-        d.y = y_probe.data_ptr() if y_probe.data_ptr() else d.x
-        descs = (_native.MctqLutTensorDesc * 1)(d)
+        descs = (_native.MctqLutTensorDesc * 1)(got[0])     # y stands in as x here: fresh outputs are at least as aligned
         return lib.mctq_lut_multi_plan_bytes(ctypes.cast(descs, c_vp), 1) > 0
 
     def __init__(self, items):
