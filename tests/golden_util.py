@@ -15,12 +15,34 @@ DT_TAG = {"float32": oracle.F32, "bfloat16": oracle.BF16, "float16": oracle.F16}
 TORCH_DT = {"float32": torch.float32, "bfloat16": torch.bfloat16, "float16": torch.float16}
 
 
+class _Arrays:
+    """Read-only view over the arrays of several .npz batches (case names are unique across batches)."""
+
+    def __init__(self, files):
+        self._files = files
+
+    def __getitem__(self, key):
+        for f in self._files:
+            if key in f.files:
+                return f[key]
+        raise KeyError(key)
+
+
 @lru_cache(maxsize=1)
 def _load():
-    with open(os.path.join(HERE, "golden", "golden_v1.json")) as f:
-        manifest = json.load(f)
-    arrays = np.load(os.path.join(HERE, "golden", "golden_v1.npz"))
-    return manifest, arrays
+    """golden_v1 (make_golden.py) + golden_v2 (make_golden_v2.py): one manifest, one array lookup."""
+    manifest, files = None, []
+    for stem in ("golden_v1", "golden_v2"):
+        with open(os.path.join(HERE, "golden", stem + ".json")) as f:
+            m = json.load(f)
+        if manifest is None:
+            manifest = m
+        else:
+            manifest["cases"] = manifest["cases"] + m["cases"]
+        files.append(np.load(os.path.join(HERE, "golden", stem + ".npz")))
+    names = [c["name"] for c in manifest["cases"]]
+    assert len(names) == len(set(names)), "duplicate golden case names"
+    return manifest, _Arrays(files)
 
 
 def manifest():
