@@ -67,7 +67,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profiler-range", action="store_true", help="bracket the timed region with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ref-batch", type=int, default=8, help="images per step of the CPU reference arm / cpu_baseline sample")
+    ap.add_argument("--ref-batch", type=int, default=64, help="images per step of the cpu_baseline sample inside the B200 arm's line "
+                    "(--impl reference itself runs the full --batch)")
+    ap.add_argument("--no-per-config", action="store_true", help="skip the C1 / C3 / C4 / C5 rows (per_config)")
     return ap.parse_args()
 
 
@@ -150,77 +152,169 @@ def make_quantizers(Q, weights):
     return wq
 
 
-def cpu_reference_step(port, torch, weights, wparams, acts, aparams):
-    """One pass of the reference's CPU torch path (ATen fake_quantize ops, exactly what the reference calls)."""
-    for w, (s, z) in zip(weights, wparams):
-        port.affine_per_channel(w, s, z, 0, -128, 127)
-    for x, (scale, zp) in zip(acts, aparams):
-        port.affine_scalar_qparams(x, scale, zp, 0, 255)
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")      # pip install --no-deps --target baseline/_ref <reference> (git-ignored, travels with gpurun)
 
 
-def build_cpu_sample(torch, port, batch, seed=1234):
+def load_reference():
+    """The UNMODIFIED reference package (sony/mct_quantizers 1.6.0) from baseline/_ref, or None when it is not installed."""
+    if not os.path.isdir(os.path.join(REF_DIR, "mct_quantizers")):
+        return None
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    try:
+        import mct_quantizers
+        if not os.path.abspath(mct_quantizers.__file__).startswith(REF_DIR):
+            return None
+        return mct_quantizers
+    except Exception:
+        return None
+
+
+def build_reference_model(torch, batch, seed=1234):
+    """BASELINE configs[1] on CPU tensors, built with the reference's own classes when baseline/_ref is importable
+    (kind "reference"), else with oracle/torch_cpu_port.py, the reference's ATen call sites restated (kind "port").
+    Returns (step, nelem, kind).  Activation ranges are the [min, max] of each tensor, as BASELINE.md C2 says."""
+    import logging
+    import warnings
+    warnings.filterwarnings("ignore")
     g = torch.Generator().manual_seed(seed)
-    weights, wparams = [], []
+    weights = []
     for shp in MBV2_WEIGHTS:
         fan_out = shp[0] * numel(shp[2:])
-        w = torch.empty(shp).normal_(0, (2.0 / fan_out) ** 0.5, generator=g)
-        thr = w.abs().flatten(1).amax(1).double().tolist()
-        s, z, _, _ = port.weights_symmetric_qparams(thr, 8)
-        weights.append(w)
-        wparams.append((s, z))
-    acts, aparams = [], []
-    for shp in MBV2_ACTS:
-        x = torch.empty((batch,) + shp).normal_(0, 1, generator=g)
-        lo, hi, scale, zp, _, _ = port.activation_uniform_qparams([-2.5], [3.0], 8)
-        acts.append(x)
-        aparams.append((scale, zp))
+        weights.append(torch.empty(shp).normal_(0, (2.0 / fan_out) ** 0.5, generator=g))
+    acts = [torch.empty((batch,) + shp).normal_(0, 1, generator=g) for shp in MBV2_ACTS]
     nelem = sum(w.numel() for w in weights) + sum(x.numel() for x in acts)
-    return weights, wparams, acts, aparams, nelem
+    ref = load_reference()
+    if ref is not None:
+        logging.getLogger("MCT Quantizers").setLevel(logging.ERROR)
+        from mct_quantizers import PytorchActivationQuantizationHolder, PytorchQuantizationWrapper, pytorch_quantizers as RQ
+        wrappers = []
+        for w in weights:
+            thr = [t if t > 0 else 1.0 for t in w.abs().flatten(1).amax(1).double().tolist()]
+            layer = torch.nn.Conv2d(1, 1, 1) if w.dim() == 4 else torch.nn.Linear(1, 1)
+            layer.weight = torch.nn.Parameter(w)
+            wrappers.append(PytorchQuantizationWrapper(layer, {'weight': RQ.WeightsSymmetricInferableQuantizer(8, thr, True, 0)}))
+        holders = [PytorchActivationQuantizationHolder(RQ.ActivationUniformInferableQuantizer(8, [float(x.min())], [float(x.max())]))
+                   for x in acts]
 
-
-def time_cpu_reference(torch, batch, min_seconds, max_reps):
+        def step():
+            out = None
+            for wr in wrappers:
+                out = wr.get_quantized_weights()            # quantize_wrapper.py:262-270 -> quantizer(w) per weight
+            for h, x in zip(holders, acts):
+                out = h(x)                                  # activation_quantization_holder.py:43-53
+            return out
+        return step, nelem, "reference"
     from oracle import torch_cpu_port as port
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    weights, wparams, acts, aparams, nelem = build_cpu_sample(torch, port, batch)
-    cpu_reference_step(port, torch, weights, wparams, acts, aparams)      # warm-up
-    best, reps, t_all = None, 0, time.perf_counter()
-    while reps < max_reps and (reps < 3 or time.perf_counter() - t_all < min_seconds):
-        t0 = time.perf_counter()
-        cpu_reference_step(port, torch, weights, wparams, acts, aparams)
-        dt = time.perf_counter() - t0
-        best = dt if best is None or dt < best else best
-        reps += 1
-    return nelem * BYTES_PER_ELEM / best / 1e9, best, reps, cores, nelem
+    wparams = [port.weights_symmetric_qparams([t if t > 0 else 1.0 for t in w.abs().flatten(1).amax(1).double().tolist()], 8)[:2]
+               for w in weights]
+    aparams = [port.activation_uniform_qparams([float(x.min())], [float(x.max())], 8)[2:4] for x in acts]
+
+    def step():
+        out = None
+        for w, (s_, z_) in zip(weights, wparams):
+            out = port.affine_per_channel(w, s_, z_, 0, -128, 127)
+        for x, (scale, zp) in zip(acts, aparams):
+            out = port.affine_scalar_qparams(x, scale, zp, 0, 255)
+        return out
+    return step, nelem, "port"
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path (its ATen call sites, restated in
-    oracle/torch_cpu_port.py because /root/reference cannot travel to the GPU box), all host threads, bounded sample."""
+    """--impl reference: the reference's own CPU implementation of the path -- the unmodified package from baseline/_ref
+    through its public API (PytorchQuantizationWrapper.get_quantized_weights, PytorchActivationQuantizationHolder.__call__)
+    on CPU tensors, all host threads, same workload as the B200 arm (53 + 53 tensors at --batch images).  The GPUs are
+    hidden from this process: the reference creates its parameters on `cuda` whenever one is visible, and this arm times
+    its CPU path."""
     rank, _, world = dist_env()
     if rank != 0:
         return
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""
     import torch
-    from oracle import torch_cpu_port as port
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    weights, wparams, acts, aparams, nelem = build_cpu_sample(torch, port, args.ref_batch)
-    for _ in range(max(args.warmup, 1)):
-        cpu_reference_step(port, torch, weights, wparams, acts, aparams)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_reference_step(port, torch, weights, wparams, acts, aparams)
-    dt = (time.perf_counter() - t0) / args.steps
+    batch = args.batch
+    try:
+        import psutil
+        while batch > 8 and numel((batch,) + (6679112,)) * 4 * 1.6 > psutil.virtual_memory().available:
+            batch //= 2                                   # host RAM guard; the sample says what ran
+    except Exception:
+        pass
+    step, nelem, kind = build_reference_model(torch, batch)
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 1)):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        dt = (time.perf_counter() - t0) / args.steps
     gbs = nelem * BYTES_PER_ELEM / dt / 1e9
-    sample = f"all 53 weight tensors + 53 activation sites at batch {args.ref_batch} ({nelem} f32 elements per step)"
+    sample = f"all 53 weight tensors + 53 activation sites at batch {batch} ({nelem} f32 elements per step)"
+    what = ("unmodified sony/mct_quantizers 1.6.0 from baseline/_ref, public API" if kind == "reference"
+            else "oracle/torch_cpu_port.py (baseline/_ref missing): the ATen ops the reference calls")
     line = {"impl": "reference", "metric": METRIC, "value": round(gbs, 3), "unit": "GB/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True,
+            "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": sample, "host": "CPU torch %s, %d threads" % (torch.__version__, cores)},
-            "cpu_baseline": {"value": round(gbs, 3), "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": WORKLOAD, "batch_per_gpu": batch, "elements_per_step_per_gpu": nelem, "sample": sample,
+                       "ranges": "ActivationUniform [min, max] of each tensor", "implementation": what,
+                       "host": "CPU torch %s, %d threads" % (torch.__version__, cores)},
+            "cpu_baseline": {"value": round(gbs, 3), "unit": "GB/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": round(gbs, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "elements_per_s": round(nelem / dt, 1)}
     print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_leg(args):
+    """cpu_baseline of the B200 arm: the reference arm itself (a fresh process with the GPUs hidden), on a bounded sample."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--batch", str(args.ref_batch), "--steps", "5", "--warmup", "1"]
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    for ln in reversed(out.stdout.strip().splitlines()):
+        if ln.startswith("{"):
+            return json.loads(ln)["cpu_baseline"]
+    raise RuntimeError("cpu_baseline leg failed: " + out.stderr[-400:])
+
+
+def verify_against_oracle(torch, wplan, weights, wq, holders, acts, last):
+    """After the timed region: windows of what the timed path produces (the last step's output, three more sites incl. the
+    largest, two weight tensors of the multi-tensor launch) against the CPU oracle, bit for bit.  oracle/ is the checker
+    only; a mismatch fails the run."""
+    import numpy as np
+    import oracle
+    checked = 0
+
+    def check_window(y, x, q, lo, hi, what):
+        nonlocal checked
+        xs = x.reshape(-1)[lo:hi].cpu().numpy()
+        ys = y.reshape(-1)[lo:hi].cpu().numpy()
+        want = oracle.fq_affine(xs, oracle.F32, np.array([q.scale], np.float64).astype(np.float32),
+                                np.array([q.zero_point], np.int32), 1, 1, 0, 255)
+        if not np.array_equal(ys.view(np.uint32), want.reshape(-1).view(np.uint32)):
+            raise RuntimeError("bench output differs from the oracle: " + what)
+        checked += hi - lo
+
+    sites = sorted(range(len(acts)), key=lambda i: acts[i].numel())
+    picked = [(len(acts) - 1, last)] + [(i, None) for i in (sites[-1], sites[len(sites) // 2], sites[0]) if i != len(acts) - 1]
+    for i, y in picked:
+        x, q = acts[i], holders[i].activation_holder_quantizer
+        y = holders[i](x) if y is None else y
+        n = x.numel()
+        w = min(n, 1 << 16)
+        for lo in sorted({0, (n // 2) // 4096 * 4096, n - w}):
+            check_window(y, x, q, lo, min(lo + w, n), f"activation site {i} [{lo}:{lo + w}]")
+    if wplan is not None:
+        outs = wplan.run()
+        for k in sorted({0, len(weights) // 2, len(weights) - 1}):
+            w, q = weights[k], wq[k]
+            want = oracle.fq_affine(w.detach().cpu().numpy(), oracle.F32, q.scales.cpu().numpy().astype(np.float32),
+                                    q.zero_points.cpu().numpy().astype(np.int32), w.shape[0], w[0].numel(), -128, 127)
+            if not np.array_equal(outs[k].cpu().numpy().reshape(-1).view(np.uint32), want.reshape(-1).view(np.uint32)):
+                raise RuntimeError(f"bench weight tensor {k} differs from the oracle")
+            checked += w.numel()
+    return {"ok": True, "elements_compared": int(checked), "against": "oracle/mctq_oracle.c (CPU restatement), bit-exact",
+            "what": "3 windows of <= 65536 elements of 4 activation sites (incl. the last timed output and the largest site) + 3 weight tensors"}
 
 
 def run_b200(args):
@@ -265,10 +359,12 @@ def run_b200(args):
     wplan = WeightPlan(triples) if triples else None
 
     acts = [torch.empty((args.batch,) + shp, device=dev).normal_(0, 1, generator=g) for shp in MBV2_ACTS]
-    holders = [mctq.PytorchActivationQuantizationHolder(Q.ActivationUniformInferableQuantizer(8, [-2.5], [3.0])).to(dev)
-               for _ in MBV2_ACTS]
+    ranges = [(float(x.min()), float(x.max())) for x in acts]        # BASELINE C2: [min, max] of the tensor
+    holders = [mctq.PytorchActivationQuantizationHolder(Q.ActivationUniformInferableQuantizer(8, [lo], [hi])).to(dev)
+               for lo, hi in ranges]
     n_w = sum(w.numel() for w in weights)
     n_a = sum(x.numel() for x in acts)
+    n_sites = len(acts)
     bytes_step = (n_w + n_a) * BYTES_PER_ELEM
 
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
@@ -370,6 +466,9 @@ def run_b200(args):
     else:
         checks = [int(chk.item())]
 
+    # ---- parity outside the timed region: windows of the timed path's outputs against the CPU oracle (the checker)
+    oracle_check = verify_against_oracle(torch, wplan, weights, wq, holders, acts, last) if rank == 0 else None
+
     # ---- e2e: same step through the public API with HOST (pinned) tensors: H2D + kernel + D2H inside the timed region
     e2e = None
     if not args.no_e2e:
@@ -431,6 +530,18 @@ def run_b200(args):
             raise RuntimeError("e2e (host-buffer) result differs from the device-resident result")
         del host_acts, host_w
 
+    # ---- the other BASELINE configs (C1 / C3 / C4 / C5), strong scaling at N > 1: tools/scale_bench.py, all ranks take part
+    per_config = None
+    if not args.no_per_config:
+        del acts, holders, last
+        torch.cuda.empty_cache()
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import scale_bench
+        rows, _ = scale_bench.run_configs(dev, rank, world, reps=5, max_gb=16.0, log=sys.stderr)
+        per_config = [{"config": r["config"], "scaling": r.get("scaling"), "kernel": r.get("kernel"), "ms": r["ms"], "GBs": r["GBs"],
+                       "GBs_per_gpu": r["GBs_per_gpu"], "pct_of_8TBs": r["pct_of_8TBs_per_gpu"],
+                       "frac_of_copy_peak": r["frac_of_copy_peak_per_gpu"]} for r in rows if "GBs" in r]
+
     if rank == 0:
         peaks = {}
         try:
@@ -466,6 +577,7 @@ def run_b200(args):
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "batch_per_gpu": args.batch, "elements_per_step_per_gpu": n_w + n_a,
                            "bytes_per_element": BYTES_PER_ELEM, "l2": "inputs larger than L2 (6.8 GB read + 6.8 GB written per step)",
+                           "ranges": "ActivationUniform [min, max] of each tensor",
                            "sharding": "activations by batch, weights by layer; no collective on the data path"},
                 "elements_per_s": round(value * 1e9 / BYTES_PER_ELEM, 1),
                 "pct_of_8TBs": round(100 * value / world / 8000.0, 2),
@@ -473,18 +585,18 @@ def run_b200(args):
                              "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                              "kernel": "%s = fq_affine_kernel<T, CH_PT, no codes, unroll 2 (8 KB tiles), fast rounding, by-value "
                                        "parameters, 16-byte vectors> (ActivationUniform sites)" % (kname or "fq_affine_kernel<float, 0, 0, 2, false, false, 16>"),
-                             "launches_per_step": len(acts),
-                             "avg_launch_us": round(act_ms / args.steps / len(acts) * 1e3, 2),
+                             "launches_per_step": n_sites,
+                             "avg_launch_us": round(act_ms / args.steps / n_sites * 1e3, 2),
                              "how": "CUDA events around every timed step minus the weights launch (%.1f us, timed separately)" % (w_ms * 1e3),
-                             "algorithmic_bytes_per_launch": int(n_a * BYTES_PER_ELEM / len(acts))},
+                             "algorithmic_bytes_per_launch": int(n_a * BYTES_PER_ELEM / n_sites)},
                 "clocks": clocks, "gpu_launches": int(launches), "checksums": checks}
         if e2e is not None:
             line["e2e"] = e2e
+        line["oracle_check"] = oracle_check
+        if per_config is not None:
+            line["per_config"] = per_config
         if not args.no_cpu_baseline and world == 1:
-            gbs, best, reps, cores, nelem = time_cpu_reference(torch, args.ref_batch, 10.0, 200)
-            line["cpu_baseline"] = {"value": round(gbs, 3), "unit": "GB/s", "cores": cores, "kind": "port",
-                                    "sample": f"all 53 weight tensors + 53 activation sites at batch {args.ref_batch} "
-                                              f"({nelem} f32 elements), best of {reps}, CPU torch ATen fake_quantize ops"}
+            line["cpu_baseline"] = cpu_baseline_leg(args)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -31,6 +31,7 @@ struct AffineArgs {
     const float* prep_soa;
     const int32_t* prep_flags;   // [0] != 0: some zero point is non-zero
     int64_t C4;
+    uint32_t early;              // loads before griddepcontrol.wait (pdl_plan_launch said the input is not the predecessor's output)
 };
 
 constexpr size_t kPrepHeaderBytes = 16;
@@ -127,8 +128,8 @@ __global__ void __launch_bounds__(kThreads) fq_affine_kernel(const AffineArgs a)
     const int64_t remaining = a.n - t0;
     const bool full = remaining >= (int64_t)TILE;
     const T* xt = reinterpret_cast<const T*>(a.x) + t0;
-    pdl_wait();
-    pdl_launch_dependents();
+    const bool early = a.early != 0;
+    pdl_gate(!early);
 
     uint32_t w[UNROLL][WORDS];
     if (full) {
@@ -147,6 +148,7 @@ __global__ void __launch_bounds__(kThreads) fq_affine_kernel(const AffineArgs a)
             }
         }
     }
+    pdl_gate(early);                                   // the tile is in flight; nothing is written before this point
 
     typename Op::ChanParams pu;
     Window win;
@@ -659,7 +661,10 @@ int launch_affine_tiles(const AffineArgs& a_in, cudaStream_t st) {
     }
     int64_t tiles = (a.n + TILE - 1) / TILE;
     if (tiles > 0x7fffffffLL) return MCTQ_E_BADARG;
-    return launch_streaming(fq_affine_kernel<T, CHMODE, CODE, UNROLL, RINT, PREP, VB>, (unsigned)tiles, smem, st, a);
+    const IoSpan in[1] = {{a.x, (size_t)a.n * sizeof(T)}};
+    const IoSpan out[2] = {{a.y, (size_t)a.n * sizeof(T)}, {a.codes, CODE == MCTQ_CODES_INT4 ? (size_t)(a.n + 1) / 2 : (size_t)a.n}};
+    a.early = (uint32_t)pdl_plan_launch(st, in, 1, out, CODE != 0 ? 2 : 1);
+    return launch_planned(fq_affine_kernel<T, CHMODE, CODE, UNROLL, RINT, PREP, VB>, (unsigned)tiles, smem, st, a);
 }
 
 // prepared parameters: TMA-staged variants (fast range, unroll 4, every code mode)

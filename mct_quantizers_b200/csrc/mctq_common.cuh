@@ -243,13 +243,29 @@ __device__ __forceinline__ void locate(uint32_t l, const Window& w, const Args& 
 
 
 // ------------------------------------------------------------------------------------------ dependent launch
-// Every streaming kernel begins with pdl_wait() (returns once the preceding kernel in the stream has completed and its
-// writes are visible; a no-op when the launch carries no programmatic-serialization attribute) and then signals
-// pdl_launch_dependents(), which lets the NEXT kernel of the stream be scheduled while this one is still running: its
-// CTAs take the SM slots that free up during our tail and sit in their own pdl_wait().  This removes the ~5 us
-// launch gap between the back-to-back fake-quant kernels of a model (54 per MobileNetV2 step).
+// Every streaming kernel is launched with the programmatic-stream-serialization attribute and brackets its work with
+// pdl_wait() (returns once the preceding kernel in the stream has completed and its writes are visible; a no-op when the
+// launch carries no programmatic dependency) and pdl_launch_dependents(), which lets the NEXT kernel of the stream be
+// scheduled while this one is still running: its CTAs take the SM slots that free up during our tail.
+//
+// Two orders exist, selected per launch by the host (`early` in the kernel arguments, see pdl_plan_launch):
+//   late  : wait -> trigger -> loads -> math -> stores     the dependent CTAs sit idle in their wait during our tail
+//   early : loads -> wait -> trigger -> math -> stores     the dependent CTAs already have their tile in flight while
+//           our last wave drains: back-to-back launches (54 per MobileNetV2 step, 96 per Llama-7B weight pass) keep the
+//           memory system busy across launch boundaries.  Only legal when the kernel's INPUT cannot be an output of the
+//           kernel it overlaps with; the trigger stays behind the wait so that at most two consecutive kernels overlap.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_gate(bool now) { if (now) { pdl_wait(); pdl_launch_dependents(); } }
+
+// Host side of the early order (mctq_host.cu): the library remembers, per (device, stream), the memory ranges its most
+// recent streaming launch WRITES.  A launch may load before the wait iff none of its inputs overlaps those ranges -- then
+// the kernel it may overlap with (the previous launch of this library on the stream, if it is still running) does not
+// produce its input.  Any other predecessor (a torch kernel, a memcpy, a launch without the attribute) has no early
+// trigger, so the dependent kernel cannot start before it completes and the order is irrelevant.  Launches whose outputs
+// are not described (multi-tensor plans) record "unknown", which forces the late order on their successor.
+struct IoSpan { const void* p; size_t bytes; };
+int pdl_plan_launch(cudaStream_t st, const IoSpan* in, int n_in, const IoSpan* out, int n_out);   // 1 = early order is safe
 
 // ------------------------------------------------------------------------------------------ TMA bulk staging
 // Parameter tables that are already laid out in global memory the way a CTA wants them in shared memory (prepared LUT
@@ -280,8 +296,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // ------------------------------------------------------------------------------------------ host helpers
 inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? 0 : (int)e; }
 
+// launch with the programmatic-serialization attribute; the caller has already declared the launch to pdl_plan_launch
 template <typename... KArgs, typename... Args>
-inline int launch_streaming(void (*kernel)(KArgs...), unsigned grid, size_t smem, cudaStream_t st, Args&&... args) {
+inline int launch_planned(void (*kernel)(KArgs...), unsigned grid, size_t smem, cudaStream_t st, Args&&... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kThreads);
@@ -295,6 +312,13 @@ inline int launch_streaming(void (*kernel)(KArgs...), unsigned grid, size_t smem
     cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cuda_rc(e);
+}
+
+// same, for kernels that always use the late order: their outputs are recorded as "unknown"
+template <typename... KArgs, typename... Args>
+inline int launch_streaming(void (*kernel)(KArgs...), unsigned grid, size_t smem, cudaStream_t st, Args&&... args) {
+    pdl_plan_launch(st, nullptr, 0, nullptr, 0);
+    return launch_planned(kernel, grid, smem, st, std::forward<Args>(args)...);
 }
 
 template <typename K>

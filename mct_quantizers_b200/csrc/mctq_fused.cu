@@ -21,6 +21,7 @@ struct FusedArgs {
     int64_t n;
     float scale;
     int32_t zp, qmin, qmax;
+    uint32_t early;          // loads before griddepcontrol.wait (see pdl_plan_launch)
 };
 
 template <typename T, int PRE>
@@ -43,8 +44,8 @@ __global__ void __launch_bounds__(kThreads) fq_affine_pre_kernel(const FusedArgs
     const bool full = remaining >= (int64_t)TILE;
     const T* xt = reinterpret_cast<const T*>(a.x) + t0;
     const T* bt = reinterpret_cast<const T*>(a.x2) + t0;
-    pdl_wait();
-    pdl_launch_dependents();
+    const bool early = a.early != 0;
+    pdl_gate(!early);
 
     uint32_t w[UNROLL][4], v[UNROLL][4];
 #pragma unroll
@@ -65,6 +66,7 @@ __global__ void __launch_bounds__(kThreads) fq_affine_pre_kernel(const FusedArgs
             if (TWO) memcpy(v[j], tb, 16);
         }
     }
+    pdl_gate(early);
 
     const float s = a.scale;
     const float inv = __fdiv_rn(1.0f, s);
@@ -121,12 +123,16 @@ using namespace mctq;
 namespace {
 
 template <typename T, int PRE>
-int launch_pre(const FusedArgs& a, cudaStream_t st) {
+int launch_pre(const FusedArgs& a_in, cudaStream_t st) {
+    FusedArgs a = a_in;
     constexpr int UNROLL = (PRE == MCTQ_PRE_ADD || PRE == MCTQ_PRE_ADD_RELU) ? 2 : 4;      // two input streams: same bytes in flight
     constexpr uint32_t TILE = kThreads * UNROLL * (16 / sizeof(T));
     const int64_t tiles = (a.n + TILE - 1) / TILE;
     if (tiles > 0x7fffffffLL) return MCTQ_E_BADARG;
-    return launch_streaming(fq_affine_pre_kernel<T, PRE, UNROLL>, (unsigned)tiles, 0, st, a);
+    const IoSpan in[2] = {{a.x, (size_t)a.n * sizeof(T)}, {a.x2, (size_t)a.n * sizeof(T)}};
+    const IoSpan out[1] = {{a.y, (size_t)a.n * sizeof(T)}};
+    a.early = (uint32_t)pdl_plan_launch(st, in, 2, out, 1);
+    return launch_planned(fq_affine_pre_kernel<T, PRE, UNROLL>, (unsigned)tiles, 0, st, a);
 }
 
 template <typename T>
@@ -159,7 +165,7 @@ int mctq_fq_affine_scalar_pre(const void* x, const void* x2, void* y, int64_t n,
     if (qmin > qmax || !((int64_t)qmax - qmin < (1 << 21)) || zp < qmin || zp > qmax) return MCTQ_E_RANGE;
     if (n == 0) return 0;
     FusedArgs a;
-    a.x = x; a.x2 = two ? x2 : nullptr; a.y = y; a.n = n; a.scale = scale; a.zp = zp; a.qmin = qmin; a.qmax = qmax;
+    a.x = x; a.x2 = two ? x2 : nullptr; a.y = y; a.n = n; a.scale = scale; a.zp = zp; a.qmin = qmin; a.qmax = qmax; a.early = 0;
     cudaStream_t st = (cudaStream_t)stream;
     switch (x_dtype) {
         case MCTQ_F32: return launch_pre_typed<float>(a, pre_op, st);

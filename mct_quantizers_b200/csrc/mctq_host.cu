@@ -1,5 +1,6 @@
 // mctq_host.cu -- process-wide state, introspection entry points and the host-buffer (staged) operators.
 #include <mutex>
+#include <stdint.h>
 
 #include "mctq_common.cuh"
 
@@ -8,10 +9,62 @@ std::atomic<int64_t> g_launches{0};
 int g_unroll = 0;           // 0 = automatic (per-tensor tiles: 2 vectors per thread, per-channel tiles: 4)
 int g_force_rint = 0;
 int g_force_ieee_div = 0;
-int g_pdl = 1;
+int g_pdl = 2;              // 0 off, 1 programmatic dependent launch (wait first), 2 + loads before the wait when provably safe
 int g_lut_shfl = 1;
 int g_wide = 1;             // 8-element vectors / 256-bit stores where a kernel has them (key 5)
 int g_multi_span = 4;       // tiles per CTA in the multi-tensor LUT launch: 1 or 4 (key 6; read when a plan is compiled)
+
+// ---- early-order bookkeeping (see mctq_common.cuh): what did the last streaming launch on (device, stream) write?
+namespace {
+struct LastLaunch {
+    cudaStream_t st;
+    int device;
+    int n_out;              // -1: outputs unknown
+    uint64_t stamp;
+    uintptr_t lo[2], hi[2];
+};
+constexpr int kLastSlots = 16;
+LastLaunch g_last[kLastSlots];
+uint64_t g_last_stamp = 0;
+std::mutex g_last_mu;
+}  // namespace
+
+int pdl_plan_launch(cudaStream_t st, const IoSpan* in, int n_in, const IoSpan* out, int n_out) {
+    if (g_pdl == 0) return 0;
+    int device = 0;
+    if (cudaGetDevice(&device) != cudaSuccess) { cudaGetLastError(); return 0; }
+    std::lock_guard<std::mutex> lock(g_last_mu);
+    LastLaunch* slot = nullptr;
+    LastLaunch* victim = &g_last[0];
+    for (int i = 0; i < kLastSlots; ++i) {
+        LastLaunch& l = g_last[i];
+        if (l.stamp && l.st == st && l.device == device) { slot = &l; break; }
+        if (l.stamp < victim->stamp) victim = &l;
+    }
+    int early = g_pdl >= 2 && in != nullptr;
+    if (slot && early) {
+        if (slot->n_out < 0) early = 0;
+        for (int i = 0; early && i < n_in; ++i) {
+            const uintptr_t lo = reinterpret_cast<uintptr_t>(in[i].p), hi = lo + in[i].bytes;
+            for (int j = 0; j < slot->n_out; ++j)
+                if (in[i].p && lo < slot->hi[j] && slot->lo[j] < hi) early = 0;
+        }
+    }
+    // a stream this table has never seen (or whose entry was evicted): the predecessor may be one of our launches that
+    // is no longer remembered -> late order
+    if (!slot) { early = 0; slot = victim; }
+    slot->st = st;
+    slot->device = device;
+    slot->stamp = ++g_last_stamp;
+    slot->n_out = out ? 0 : -1;
+    for (int j = 0; out && j < n_out && j < 2; ++j) {
+        if (!out[j].p) continue;
+        slot->lo[slot->n_out] = reinterpret_cast<uintptr_t>(out[j].p);
+        slot->hi[slot->n_out] = slot->lo[slot->n_out] + out[j].bytes;
+        ++slot->n_out;
+    }
+    return early;
+}
 }  // namespace mctq
 
 using namespace mctq;
@@ -32,7 +85,7 @@ int mctq_set_tuning(int key, int value) {
         case 0: prev = g_unroll; if (value != 0 && value != 2 && value != 4 && value != 8) return MCTQ_E_BADARG; g_unroll = value; return prev;
         case 1: prev = g_force_rint; g_force_rint = value ? 1 : 0; return prev;
         case 2: prev = g_force_ieee_div; g_force_ieee_div = value ? 1 : 0; return prev;
-        case 3: prev = g_pdl; g_pdl = value ? 1 : 0; return prev;
+        case 3: prev = g_pdl; if (value < 0 || value > 2) return MCTQ_E_BADARG; g_pdl = value; return prev;
         case 4: prev = g_lut_shfl; g_lut_shfl = value ? 1 : 0; return prev;
         case 5: prev = g_wide; if (value < 0 || value > 2) return MCTQ_E_BADARG; g_wide = value; return prev;
         case 6: prev = g_multi_span; if (value != 1 && value != 4) return MCTQ_E_BADARG; g_multi_span = value; return prev;

@@ -54,6 +54,13 @@ def _ptr(t):
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
 _get_device = getattr(torch._C, "_cuda_getDevice", None)
 _set_device = getattr(torch._C, "_cuda_setDevice", None)
+if _raw_stream is None:                      # private fast paths missing in this torch build: public equivalents
+    def _raw_stream(index):
+        return torch.cuda.current_stream(index).cuda_stream
+if _get_device is None:
+    _get_device = torch.cuda.current_device
+if _set_device is None:
+    _set_device = torch.cuda.set_device
 
 
 def _stream(device):
@@ -158,8 +165,28 @@ def _check_channel_params(x, scale, zp, axis):
         raise RuntimeError("dimensions of scale and zero-point are not consistent with input tensor")
 
 
+def _ver(t):
+    """Version counter of a parameter tensor for cache keys; inference tensors have none (and cannot be edited in place
+    outside inference mode), so they get a constant."""
+    return -1 if t.is_inference() else t._version
+
+
+_PARAM_COPIES = {}        # (data_ptr, version, numel, dtype, src device, dst device) -> (source kept alive, copy)
+
+
 def _param_on(t, device):
-    return t if t.device == device else t.to(device, non_blocking=True)
+    """`t` on `device`.  Cross-device copies are cached: a fresh copy per call would also defeat the prepared-parameter
+    caches below (their keys hold the copy's data_ptr) and re-prepare on every call."""
+    if t.device == device:
+        return t
+    key = (t.data_ptr(), _ver(t), t.numel(), t.dtype, str(t.device), str(device))
+    hit = _PARAM_COPIES.get(key)
+    if hit is None:
+        if len(_PARAM_COPIES) >= 1024:
+            _PARAM_COPIES.clear()
+        hit = (t, t.to(device, non_blocking=True))
+        _PARAM_COPIES[key] = hit
+    return hit[1]
 
 
 _staging = {}
@@ -281,7 +308,7 @@ def clear_affine_caches():
 def _affine_prepared(lib, scale, zero_point, index):
     """Device blob of prepared parameters for (scale, zero_point), built once per parameter pair; None while a CUDA
     graph is being captured and the blob does not exist yet (the raw-parameter entry point is used instead)."""
-    key = (scale.data_ptr(), zero_point.data_ptr(), scale._version, zero_point._version, scale.numel(), index)
+    key = (scale.data_ptr(), zero_point.data_ptr(), _ver(scale), _ver(zero_point), scale.numel(), index)
     ent = _AFFINE_PREPARED.get(key)
     if ent is None:
         if torch.cuda.is_current_stream_capturing():
@@ -430,6 +457,7 @@ _ROUND_TAG = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 def clear_lut_caches():
     _LUT_DEV_TABLES.clear()
     _LUT_PREPARED.clear()
+    _PARAM_COPIES.clear()
 
 
 def _table_header(table_cpu):
@@ -461,15 +489,17 @@ def _prepared_for(table, K, device, thr_dev, eps, scalar, divisor, thr_f32, roun
     if table.device.type != 'cpu':
         return None
     if scalar:
-        key = (table.data_ptr(), str(device), 's', float(divisor), float(thr_f32), int(round_dtype))
+        key = (table.data_ptr(), int(K), str(device), 's', float(divisor), float(thr_f32), int(round_dtype))
         C = 1
     else:
-        key = (table.data_ptr(), str(device), 't', thr_dev.data_ptr(), thr_dev.numel(), float(eps))
+        key = (table.data_ptr(), int(K), str(device), 't', thr_dev.data_ptr(), _ver(thr_dev), thr_dev.numel(), float(eps))
         C = thr_dev.numel()
     hit = _LUT_PREPARED.get(key)
     if hit is None:
         if torch.cuda.is_current_stream_capturing():
             return None                     # preparation synchronises: not inside a CUDA-graph capture (generic kernel instead)
+        if len(_LUT_PREPARED) >= 1024:      # bounded like _AFFINE_PREPARED: entries pin a threshold tensor and a device blob
+            _LUT_PREPARED.clear()
         lib = _native.load()
         bw, signed = _table_header(table)
         nbytes = lib.mctq_lut_prepared_bytes(int(K), bw, signed, C)
@@ -544,7 +574,7 @@ def lut_weights_direct(x, table, K, threshold, per_channel, axis, eps, cache):
     device).  `cache` is a dict owned by the quantizer: (shape, dtype, device, thr ptr) -> launch constants.  Anything
     unusual (non-contiguous input, no prepared blob, misaligned view) goes through the general path."""
     if x.is_contiguous() and x.numel():
-        key = (x.shape, x.dtype, x.device, threshold.data_ptr())
+        key = (x.shape, x.dtype, x.device, threshold.data_ptr(), _ver(threshold))
         hit = cache.get(key)
         if hit is None:
             hit = False
@@ -812,6 +842,25 @@ class MultiTensorPlan:
     Build once from [(x, scale, zp, axis, qmin, qmax)] (all CUDA, same device): outputs are allocated here and
     reused by every run(); the descriptor table is uploaded once.  run() enqueues ONE kernel on the current
     stream.  Reference loop being replaced: quantize_wrapper.py:228-240 / :260-270."""
+
+    @staticmethod
+    def accepts(item):
+        """Whether a tensor can be part of a plan: CUDA, supported dtype, non-empty, dense in memory (the plan captures
+        pointers, so no hidden copies), parameters of the right length."""
+        x, scale, zp, axis, qmin, qmax = item
+        if not x.is_cuda or x.dtype not in _DT or x.numel() == 0 or not _is_dense_permutation(x):
+            return False
+        try:
+            if axis is None:
+                if scale.numel() != 1 or zp.numel() != 1:
+                    return False
+                xd = _dense(x)
+            else:
+                _check_channel_params(x, scale, zp, axis)
+                xd = _channel_layout(x, axis)[0]
+        except (RuntimeError, IndexError):
+            return False
+        return xd.data_ptr() == x.data_ptr() and scale.dtype == torch.float32 and zp.dtype == torch.int32
 
     def __init__(self, items):
         lib = _native.load()

@@ -59,13 +59,15 @@ class PytorchFusedActivationQuantizationHolder(PytorchActivationQuantizationHold
         two = self.pre_op in ("add", "add_relu")
         if two and other is None:
             raise TypeError(f"pre_op {self.pre_op!r} needs two inputs")
+        scale, zp, qmin, qmax = affine_scalar_params(q)
         fusable = inputs.is_cuda and not (q._use_custom_impl and torch.jit.is_tracing()) and \
+            int(qmax) - int(qmin) < (1 << 21) and \
             (not two or (torch.is_tensor(other) and other.shape == inputs.shape and other.dtype == inputs.dtype
                          and other.device == inputs.device))
         if not fusable:
-            # broadcasting adds, host tensors, ONNX export: the plain pair (each op still runs on the GPU)
+            # broadcasting adds, host tensors, ONNX export, ranges of 2^21 codes or more (outside the fused kernel's fast
+            # rounding): the plain pair (each op still runs on the GPU)
             return self._unfused(inputs, other)
-        scale, zp, qmin, qmax = affine_scalar_params(q)
         code = PRE_OPS[self.pre_op]
         if ops.direct_ok(inputs):
             with torch.no_grad():
@@ -79,8 +81,29 @@ _RELU6_FUNCS = {F.relu6}
 _ADD_FUNCS = {operator.add, torch.add}
 
 
+def _is_inplace(node, modules):
+    """relu_(x) spellings: nn.ReLU(inplace=True), F.relu(x, inplace=True) / F.relu(x, True), x.relu_()."""
+    if node.op == "call_module":
+        return bool(getattr(modules.get(node.target), "inplace", False))
+    if node.op == "call_function":
+        return bool(node.kwargs.get("inplace", False)) or (len(node.args) > 1 and node.args[1] is True)
+    return node.op == "call_method" and str(node.target).endswith("_")
+
+
 def _kind(node, modules):
-    """'relu' / 'relu6' / 'add' when `node` is a fusable producer, else None."""
+    """'relu' / 'relu6' / 'add' when `node` is a fusable producer, else None.  An IN-PLACE relu mutates its input: it is
+    only fusable when nobody else can observe that input (the input node has this relu as its only user and is not a
+    graph input), because the fused kernel leaves the input untouched."""
+    if node.op in ("call_module", "call_function", "call_method") and _is_inplace(node, modules):
+        src = node.args[0] if node.args else None
+        if not isinstance(src, torch.fx.Node) or len(src.users) != 1 or src.op in ("placeholder", "get_attr"):
+            return None
+        if node.op == "call_function":
+            if set(node.kwargs) - {"inplace"} or len(node.args) > 2:
+                return None
+            return "relu" if node.target in _RELU_FUNCS else ("relu6" if node.target in _RELU6_FUNCS else None)
+    elif node.op == "call_function" and node.kwargs and set(node.kwargs) != {"inplace"}:
+        return None
     if node.op == "call_module":
         m = modules.get(node.target)
         if isinstance(m, torch.nn.ReLU):
@@ -89,9 +112,9 @@ def _kind(node, modules):
             return "relu6"
         return None
     if node.op == "call_function":
-        if node.target in _RELU_FUNCS and len(node.args) == 1:
+        if node.target in _RELU_FUNCS and len(node.args) in (1, 2):
             return "relu"
-        if node.target in _RELU6_FUNCS and len(node.args) == 1:
+        if node.target in _RELU6_FUNCS and len(node.args) in (1, 2):
             return "relu6"
         if node.target in _ADD_FUNCS and len(node.args) == 2 and not node.kwargs and \
                 all(isinstance(a, torch.fx.Node) for a in node.args):

@@ -38,39 +38,91 @@ def plan_for(weight_vars) -> "WeightPlan":
     return WeightPlan(weight_vars)
 
 
+def _signature(w, q):
+    """What a plan captured of one (weight, quantizer) pair: storage, placement and layout of the weight plus the identity and
+    in-place version of the quantizer's parameter tensors.  A plan whose signatures no longer match the live objects
+    (model.to(), .half(), load_state_dict into new storage, a re-assigned parameter, edited thresholds) is rebuilt."""
+    sig = [w.data_ptr(), w.device, w.dtype, tuple(w.shape), tuple(w.stride())]
+    for name in ('scales', 'zero_points', '_threshold_torch'):
+        t = q.__dict__.get(name)
+        if isinstance(t, torch.Tensor):
+            sig += [t.data_ptr(), -1 if t.is_inference() else t._version]
+    return tuple(sig)
+
+
 class WeightPlan:
-    """Pre-built launch plan over (name, weight, quantizer) triples.  Keeps output buffers; run() refreshes them."""
+    """Launch plan over (name, weight, quantizer) triples: one multi-tensor launch per quantizer family and device.
+    Output buffers are kept and refreshed by run().
+
+    The plan captures raw pointers, so run() first compares every triple's live signature (storage pointer, device, dtype,
+    shape, strides, parameter tensors) with what was captured and REBUILDS when anything moved -- after `model.to()`,
+    `.half()` or a re-assigned parameter the stale storage is never quantized.  Tensors a multi-tensor launch cannot take
+    (non-dense views, CPU tensors, user-defined quantizers, uniform quantizers whose zero point leaves the range: the
+    per-layer call raises the reference's error) go through their quantizer's own `__call__`, which also owns the
+    reuse contract (`enable_reuse` / `resue_outputs`)."""
 
     def __init__(self, weight_vars):
-        self.names, self.fused_idx, self.lut_idx, self.other = [], [], [], []
-        items, lut_items = [], []
-        for k, (name, w, q) in enumerate(weight_vars):
-            self.names.append(name)
-            ok_dtype = w.is_cuda and w.dtype in (torch.float32, torch.bfloat16, torch.float16)
-            lut_item = _lut_item(q, w) if ok_dtype else None
-            if _is_affine_weight_quantizer(q) and ok_dtype:
-                w.requires_grad = False
+        self.vars = [(name, w, q) for name, w, q in weight_vars]
+        self.names = [name for name, _, _ in self.vars]
+        self.n = len(self.vars)
+        self._build()
+
+    def _build(self):
+        self.fused_idx, self.lut_idx, self.other = [], [], []
+        self._plans, self._lut_plans = [], []                     # [(indices, plan)] per device
+        by_dev, lut_by_dev = {}, {}
+        for k, (name, w, q) in enumerate(self.vars):
+            ok_dtype = w.is_cuda and w.dtype in (torch.float32, torch.bfloat16, torch.float16) and w.numel() > 0
+            reuse = bool(q.__dict__.get('enable_reuse', False))
+            item = None
+            if ok_dtype and not reuse and _is_affine_weight_quantizer(q) and not q.__dict__.get('_zero_point_out_of_range', False):
                 scales, zps = q._on(w.device, q.scales, q.zero_points)
-                items.append((w.detach(), scales.flatten(), zps.flatten(), q.channel_axis if q.per_channel else None,
-                              q.min_quantized_domain, q.max_quantized_domain))
-                self.fused_idx.append(k)
-            elif lut_item is not None:
+                item = (w.detach(), scales.flatten(), zps.flatten(), q.channel_axis if q.per_channel else None,
+                        q.min_quantized_domain, q.max_quantized_domain)
+                if MultiTensorPlan.accepts(item):
+                    w.requires_grad = False
+                    by_dev.setdefault(w.device, ([], []))
+                    by_dev[w.device][0].append(k)
+                    by_dev[w.device][1].append(item)
+                    self.fused_idx.append(k)
+                    continue
+            lut_item = _lut_item(q, w) if ok_dtype and not reuse else None
+            if lut_item is not None:
                 w.requires_grad = False
-                lut_items.append(lut_item)
+                lut_by_dev.setdefault(w.device, ([], []))
+                lut_by_dev[w.device][0].append(k)
+                lut_by_dev[w.device][1].append(lut_item)
                 self.lut_idx.append(k)
             else:
                 self.other.append((k, w, q))
-        self.plan = MultiTensorPlan(items) if items else None
-        self.lut_plan = LutMultiPlan(lut_items) if lut_items else None
-        self.n = len(weight_vars)
+        for dev, (idx, items) in by_dev.items():
+            self._plans.append((idx, MultiTensorPlan(items)))
+        for dev, (idx, items) in lut_by_dev.items():
+            self._lut_plans.append((idx, LutMultiPlan(items)))
+        self._sigs = [_signature(w, q) + (bool(q.__dict__.get('enable_reuse', False)),) for _, w, q in self.vars]
+
+    # first plan of each family (single-device models: the only one)
+    @property
+    def plan(self):
+        return self._plans[0][1] if self._plans else None
+
+    @property
+    def lut_plan(self):
+        return self._lut_plans[0][1] if self._lut_plans else None
+
+    def stale(self) -> bool:
+        return any(_signature(w, q) + (bool(q.__dict__.get('enable_reuse', False)),) != sig
+                   for (_, w, q), sig in zip(self.vars, self._sigs))
 
     def run(self) -> List[torch.Tensor]:
+        if self.stale():
+            self._build()
         out = [None] * self.n
-        if self.plan is not None:
-            for k, y in zip(self.fused_idx, self.plan.run()):
+        for idx, plan in self._plans:
+            for k, y in zip(idx, plan.run()):
                 out[k] = y
-        if self.lut_plan is not None:
-            for k, y in zip(self.lut_idx, self.lut_plan.run()):
+        for idx, plan in self._lut_plans:
+            for k, y in zip(idx, plan.run()):
                 out[k] = y
         for k, w, q in self.other:
             out[k] = q(w)
@@ -118,20 +170,31 @@ class ModelWeightPlan:
 
     def __init__(self, model: torch.nn.Module):
         from mct_quantizers_b200.pytorch.quantize_wrapper import PytorchQuantizationWrapper
-        self.wrappers, triples, self._owner = [], [], []
-        for mod in model.modules():
-            if isinstance(mod, PytorchQuantizationWrapper) and mod.is_weights_quantization:
-                self.wrappers.append(mod)
-                for name, w, q in mod.get_weights_vars():
-                    triples.append((name, w, q))
-                    self._owner.append(mod)
-        self.plan = WeightPlan(triples) if triples else None
+        self.wrappers = [mod for mod in model.modules()
+                         if isinstance(mod, PytorchQuantizationWrapper) and mod.is_weights_quantization]
+        self.plan = None
+        self._collect()
         self.active = False
 
+    def _collect(self):
+        """(Re)build the plan from the wrappers' CURRENT weight variables."""
+        triples, self._owner = [], []
+        for mod in self.wrappers:
+            for name, w, q in mod.get_weights_vars():
+                triples.append((name, w, q))
+                self._owner.append(mod)
+        self._ids = [(id(w), id(q)) for _, w, q in triples]
+        self.plan = WeightPlan(triples) if triples else None
+
     def refresh(self):
-        """Quantize every weight (one launch for the affine quantizers) and install the results."""
+        """Quantize every weight (one launch per quantizer family and device) and install the results.  The wrappers'
+        weight variables are looked at again on every refresh: re-assigned parameters or quantizers rebuild the plan, moved
+        / converted storage (`model.to()`, `.half()`) is caught by WeightPlan's signature check."""
         if self.plan is None:
             return
+        live = [(id(w), id(q)) for mod in self.wrappers for _, w, q in mod.get_weights_vars()]
+        if live != self._ids:
+            self._collect()
         per_wrapper = {}
         for owner, name, y in zip(self._owner, self.plan.names, self.plan.run()):
             per_wrapper.setdefault(id(owner), (owner, {}))[1][name] = y

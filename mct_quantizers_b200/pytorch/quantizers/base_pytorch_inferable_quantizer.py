@@ -41,9 +41,10 @@ class BasePyTorchInferableQuantizer(BaseInferableQuantizer):
                 out.append(t)
                 continue
             key = (id(t), str(device))
+            ver = -1 if t.is_inference() else t._version      # inference tensors carry no version counter
             hit = self._per_device.get(key)
-            if hit is None or hit[0] is not t:
-                hit = (t, t.to(device))
+            if hit is None or hit[0] is not t or hit[2] != ver:      # a new tensor object, or edited in place since the copy
+                hit = (t, t.to(device), ver)
                 self._per_device[key] = hit
             out.append(hit[1])
         return out

@@ -55,6 +55,35 @@ def test_fx_pass_structure():
     assert sum(1 for n in gm2.graph.nodes if n.op == "call_function" and "fq_affine_scalar_pre" in str(n.target)) == 4
 
 
+class InplaceBlock(torch.nn.Module):
+    """In-place relus: fusable only when nobody else can observe the mutated input."""
+
+    def __init__(self):
+        super().__init__()
+        self.lin = torch.nn.Linear(8, 8)
+        self.relu_ = torch.nn.ReLU(inplace=True)
+        self.h1 = mctq.PytorchActivationQuantizationHolder(Q.ActivationUniformInferableQuantizer(8, [0.0], [6.0]))
+        self.h2 = mctq.PytorchActivationQuantizationHolder(Q.ActivationUniformInferableQuantizer(8, [0.0], [6.0]))
+        self.h3 = mctq.PytorchActivationQuantizationHolder(Q.ActivationUniformInferableQuantizer(8, [0.0], [6.0]))
+        self.h4 = mctq.PytorchActivationQuantizationHolder(Q.ActivationUniformInferableQuantizer(8, [0.0], [6.0]))
+
+    def forward(self, x):
+        a = self.h1(self.relu_(self.lin(x)))                           # private intermediate, in place: fuses
+        t = self.lin(a)
+        b = self.h2(torch.nn.functional.relu(t, inplace=True))         # t is read again below (after its mutation): stays
+        c = self.h3(torch.nn.functional.relu(self.lin(b), inplace=True))   # private intermediate: fuses
+        d = self.h4(self.relu_(x))                                     # would mutate a graph input: stays
+        return a + b + c + d + t
+
+
+def test_fx_pass_leaves_observable_inplace_relus_alone():
+    torch.manual_seed(0)
+    gm = mctq.fuse_activation_producers(InplaceBlock())
+    targets = [str(n.target) for n in gm.graph.nodes if n.op == "call_module"]
+    assert gm.mctq_fused_sites == 2
+    assert "h2" in targets and "h4" in targets and "h1" not in targets and "h3" not in targets
+
+
 def test_fused_holder_argument_errors():
     with pytest.raises(ValueError):
         PytorchFusedActivationQuantizationHolder(Q.ActivationSymmetricInferableQuantizer(8, [4.0], True), "gelu")
