@@ -277,7 +277,7 @@ def cpu_baseline_leg(args):
     raise RuntimeError("cpu_baseline leg failed: " + out.stderr[-400:])
 
 
-def verify_against_oracle(torch, wplan, weights, wq, holders, acts, last):
+def verify_against_oracle(torch, wplan, weights, wq, holders, acts, last, aplan):
     """After the timed region: windows of what the timed path produces (the last step's output, three more sites incl. the
     largest, two weight tensors of the multi-tensor launch) against the CPU oracle, bit for bit.  oracle/ is the checker
     only; a mismatch fails the run."""
@@ -299,7 +299,7 @@ def verify_against_oracle(torch, wplan, weights, wq, holders, acts, last):
     picked = [(len(acts) - 1, last)] + [(i, None) for i in (sites[-1], sites[len(sites) // 2], sites[0]) if i != len(acts) - 1]
     for i, y in picked:
         x, q = acts[i], holders[i].activation_holder_quantizer
-        y = holders[i](x) if y is None else y
+        y = aplan.outputs_of(i) if y is None else y         # what the timed launch wrote for this site
         n = x.numel()
         w = min(n, 1 << 16)
         for lo in sorted({0, (n // 2) // 4096 * 4096, n - w}):
@@ -367,9 +367,20 @@ def run_b200(args):
     n_sites = len(acts)
     bytes_step = (n_w + n_a) * BYTES_PER_ELEM
 
+    # every activation site's input exists up front in this workload, so the sites run as ONE launch (ActivationPlan ->
+    # mctq_fq_affine_scalar_multi), like the weights (WeightPlan -> mctq_fq_affine_multi): 2 launches per step.  The same
+    # step as 53 holder calls (one launch each) is timed after it and reported as `per_call`.
+    aplan = mctq.ActivationPlan(list(zip(holders, acts)))
+    assert not aplan.other and len(aplan._plans) == 1
+
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
 
     def step():
+        if wplan is not None:
+            wplan.run()
+        return aplan.run()[-1]
+
+    def step_per_call():
         if wplan is not None:
             wplan.run()
         out = None
@@ -409,14 +420,17 @@ def run_b200(args):
     w_ms = 0.0
     if wplan is not None:
         wa, wb = ev(), ev()
-        reps_w = 20
+        reps_w = 6
         wplan.run()
-        wa.record()
+        big = max(range(len(acts)), key=lambda i: acts[i].numel())
+        keep = [holders[big](acts[big]) for _ in range(8)]          # ~2.8 ms of queued GPU work: the host runs ahead, so the
+        wa.record()                                                  # events bracket back-to-back kernels, not host time
         for _ in range(reps_w):
             wplan.run()
         wb.record()
         wb.synchronize()
         w_ms = wa.elapsed_time(wb) / reps_w
+        del keep
     launches0 = lib.mctq_launch_count()
     e0, e1 = ev(), ev()
     step_ev = [ev() for _ in range(args.steps + 1)]
@@ -457,6 +471,48 @@ def run_b200(args):
     value = tot_bytes.item() / (ms_step * 1e-3) / 1e9
     clocks = sampler.summary()
 
+    # ---- the same step as per-holder calls (53 + 1 launches), same timing rules
+    torch.cuda.synchronize()
+    for _ in range(3):
+        last_pc = step_per_call()
+    barrier()
+    pc0, pc1 = ev(), ev()
+    pc0.record()
+    pc_l0 = lib.mctq_launch_count()
+    for _ in range(args.steps):
+        last_pc = step_per_call()
+    pc1.record()
+    barrier()
+    pc_launches = lib.mctq_launch_count() - pc_l0
+    tpc = torch.tensor([pc0.elapsed_time(pc1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tpc, op=dist.ReduceOp.MAX)
+    pc_ms = tpc.item() / args.steps
+    if sharding.checksum64(last_pc) != sharding.checksum64(last):
+        raise RuntimeError("one-launch ActivationPlan result differs from the per-holder result")
+    per_call = {"value": round(tot_bytes.item() / (pc_ms * 1e-3) / 1e9, 2), "unit": "GB/s", "ms_per_step": round(pc_ms, 4),
+                "gpu_launches": int(pc_launches), "pct_of_8TBs": round(100 * tot_bytes.item() / (pc_ms * 1e-3) / 1e9 / world / 8000.0, 2),
+                "what": "the same step as 53 PytorchActivationQuantizationHolder calls (one launch each, programmatic dependent launch) "
+                        "+ the weights launch"}
+    # ... and inside `with private_stream():` (opt-in early order: these inputs exist before the step starts)
+    with mctq.private_stream():
+        for _ in range(3):
+            last_pc = step_per_call()
+        barrier()
+        pp0, pp1 = ev(), ev()
+        pp0.record()
+        for _ in range(args.steps):
+            last_pc = step_per_call()
+        pp1.record()
+        barrier()
+    tpp = torch.tensor([pp0.elapsed_time(pp1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tpp, op=dist.ReduceOp.MAX)
+    per_call["private_stream_value"] = round(tot_bytes.item() / (tpp.item() / args.steps * 1e-3) / 1e9, 2)
+    if sharding.checksum64(last_pc) != sharding.checksum64(last):
+        raise RuntimeError("private_stream() result differs")
+    del last_pc
+
     # ---- verification outside the timed region: checksums gathered with NCCL (no data-path collective)
     chk = torch.tensor([sharding.checksum64(last)], device=dev, dtype=torch.int64)
     if world > 1:
@@ -467,7 +523,7 @@ def run_b200(args):
         checks = [int(chk.item())]
 
     # ---- parity outside the timed region: windows of the timed path's outputs against the CPU oracle (the checker)
-    oracle_check = verify_against_oracle(torch, wplan, weights, wq, holders, acts, last) if rank == 0 else None
+    oracle_check = verify_against_oracle(torch, wplan, weights, wq, holders, acts, last, aplan) if rank == 0 else None
 
     # ---- e2e: same step through the public API with HOST (pinned) tensors: H2D + kernel + D2H inside the timed region
     e2e = None
@@ -533,7 +589,7 @@ def run_b200(args):
     # ---- the other BASELINE configs (C1 / C3 / C4 / C5), strong scaling at N > 1: tools/scale_bench.py, all ranks take part
     per_config = None
     if not args.no_per_config:
-        del acts, holders, last
+        del acts, holders, last, aplan
         torch.cuda.empty_cache()
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import scale_bench
@@ -561,10 +617,10 @@ def run_b200(args):
                 cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_bench_traffic.json")))
                 with open(cands[-1]) as f:                       # the newest round's capture
                     for k, v in json.load(f).items():
-                        if k.startswith("fq_affine_kernel<float, 0, 0,"):       # <float, CH_PT, no codes, ...>
+                        if k.startswith("fq_affine_sites_kernel"):
                             traffic = int(v["dram_bytes_per_launch"])
                             kname = k
-                            traffic_src = ("profiles/%s (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the 53 launches "
+                            traffic_src = ("profiles/%s (ncu dram__bytes_read.sum + dram__bytes_write.sum of the one launch "
                                            "of a step)" % os.path.basename(cands[-1]))
         except Exception:
             pass
@@ -583,13 +639,13 @@ def run_b200(args):
                 "pct_of_8TBs": round(100 * value / world / 8000.0, 2),
                 "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                              "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                             "kernel": "%s = fq_affine_kernel<T, CH_PT, no codes, unroll 2 (8 KB tiles), fast rounding, by-value "
-                                       "parameters, 16-byte vectors> (ActivationUniform sites)" % (kname or "fq_affine_kernel<float, 0, 0, 2, false, false, 16>"),
-                             "launches_per_step": n_sites,
-                             "avg_launch_us": round(act_ms / args.steps / n_sites * 1e3, 2),
+                             "kernel": "fq_affine_sites_kernel (all 53 ActivationUniform sites in one grid: per-tensor body of fq_affine_kernel<T, CH_PT>, "
+                                       "8 KB tiles, site table in kernel parameters)",
+                             "launches_per_step": 1,
+                             "avg_launch_us": round(act_ms / args.steps * 1e3, 2),
                              "how": "CUDA events around every timed step minus the weights launch (%.1f us, timed separately)" % (w_ms * 1e3),
-                             "algorithmic_bytes_per_launch": int(n_a * BYTES_PER_ELEM / n_sites)},
-                "clocks": clocks, "gpu_launches": int(launches), "checksums": checks}
+                             "algorithmic_bytes_per_launch": int(n_a * BYTES_PER_ELEM), "sites_per_launch": n_sites},
+                "clocks": clocks, "gpu_launches": int(launches), "per_call": per_call, "checksums": checks}
         if e2e is not None:
             line["e2e"] = e2e
         line["oracle_check"] = oracle_check

@@ -148,6 +148,27 @@ int64_t mctq_multi_plan(const MctqTensorDesc* descs_host, int n_desc, int32_t* t
 int mctq_fq_affine_multi(const MctqTensorDesc* descs_dev, const int32_t* tile_starts_dev, int n_desc,
                          int64_t total_tiles, void* stream);
 
+/* Many per-tensor (scalar-parameter) sites in ONE launch: the activation holders of a model whose inputs already exist
+ * (calibration / analysis passes, batched serving of independent tensors).
+ * Replaces: a loop of PytorchActivationQuantizationHolder.forward calls, each one
+ *           torch.fake_quantize_per_tensor_affine(x, scale: float, zero_point: int, quant_min, quant_max)
+ *           (mct_quantizers/pytorch/activation_quantization_holder.py:43-53 ->
+ *            activation_symmetric_inferable_quantizer.py:113-117 / activation_uniform_inferable_quantizer.py:124-128).
+ * `sites` is a HOST array (it travels as kernel parameters, 64 sites per launch); x / y are device pointers, 16-byte
+ * aligned, y has x's dtype; arithmetic identical to mctq_fq_affine_scalar.  Sites with n == 0 are skipped. */
+typedef struct MctqSiteDesc {
+    const void* x;
+    void* y;
+    int64_t n;
+    int32_t dtype;
+    float scale;
+    int32_t zp;
+    int32_t qmin;
+    int32_t qmax;
+    int32_t reserved;
+} MctqSiteDesc;
+int mctq_fq_affine_scalar_multi(const MctqSiteDesc* sites_host, int n_sites, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------
  * LUT (nearest-centroid) fake-quant.
  * Replaces: lut_quantizer(...)  mct_quantizers/pytorch/quantizer_utils.py:95-139 (which calls
@@ -257,7 +278,10 @@ int mctq_fq_lut_host(const void* x_host, float* y_host, int64_t n, int x_dtype,
 /* launches of this library's kernels since load (what bench.py reports as gpu_launches) */
 int64_t mctq_launch_count(void);
 /* variant selection for experiments: key 0 = unroll (0 = automatic [default], 2, 4, 8), key 1 = force rint path (0/1),
- * key 2 = force IEEE-division LUT path (0/1), key 3 = programmatic dependent launch (default 1),
+ * key 2 = force IEEE-division LUT path (0/1), key 3 = programmatic dependent launch: 0 off, 1 wait-then-load (default),
+ *   2 = load-then-wait for launches whose input is not an output of this library's previous launch on the stream -- only
+ *   legal while NO other library's kernels feed these launches on that stream (they may release their dependents before
+ *   their stores are visible); opt-in, see mct_quantizers_b200.private_stream(),
  * key 4 = warp-shuffle search in the generic LUT kernel for tables of <= 32 entries (default 1),
  * key 5 = wide vectors (8 elements per vector, 256-bit stores) in the kernels that have them (default 1),
  * key 6 = tiles per CTA of the multi-tensor LUT launch, 1 or 4 (default 4; read by mctq_lut_multi_plan);

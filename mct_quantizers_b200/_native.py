@@ -35,6 +35,12 @@ class MctqLutTensorDesc(ctypes.Structure):
                 ("dtype", c_i32), ("K", c_i32), ("lut_values_bitwidth", c_i32), ("is_signed", c_i32)]
 
 
+class MctqSiteDesc(ctypes.Structure):
+    """Mirror of `struct MctqSiteDesc` (include/mctq.h)."""
+    _fields_ = [("x", c_vp), ("y", c_vp), ("n", c_i64), ("dtype", c_i32), ("scale", c_f32), ("zp", c_i32),
+                ("qmin", c_i32), ("qmax", c_i32), ("reserved", c_i32)]
+
+
 # name -> (restype, argtypes): every symbol include/mctq.h declares
 SIGNATURES = {
     "mctq_abi_version": (c_int, []),
@@ -49,6 +55,7 @@ SIGNATURES = {
     "mctq_multi_tile_elems": (c_i64, []),
     "mctq_multi_plan": (c_i64, [c_vp, c_int, c_vp]),
     "mctq_fq_affine_multi": (c_int, [c_vp, c_vp, c_int, c_i64, c_vp]),
+    "mctq_fq_affine_scalar_multi": (c_int, [c_vp, c_int, c_vp]),
     "mctq_lut_table_bytes": (c_sz, [c_int]),
     "mctq_lut_build_table": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_sz]),
     "mctq_fq_lut": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_i64, c_i64, c_i64, c_f32, c_int, c_vp]),

@@ -31,7 +31,7 @@ struct AffineArgs {
     const float* prep_soa;
     const int32_t* prep_flags;   // [0] != 0: some zero point is non-zero
     int64_t C4;
-    uint32_t early;              // loads before griddepcontrol.wait (pdl_plan_launch said the input is not the predecessor's output)
+    uint32_t early;              // loads before griddepcontrol.wait (opt-in; pdl_plan_launch found the input is not the predecessor's output)
 };
 
 constexpr size_t kPrepHeaderBytes = 16;
@@ -616,6 +616,95 @@ __global__ void __launch_bounds__(kThreads) fq_affine_multi_kernel(const MctqTen
     else { if (fast) multi_tile_body<__half, false>(d, e0); else multi_tile_body<__half, true>(d, e0); }
 }
 
+// ---- many per-tensor sites, one launch (activation holders whose inputs already exist; SURVEY 8f rank 1 applied to the
+// activation side).  54 back-to-back launches of a MobileNetV2 step lose ~1.5 us each to the drain of one grid and the
+// ramp of the next even with programmatic dependent launch (4 % of the step); one grid over all sites has neither.
+// The site table travels as kernel parameters (constant bank: a binary search of a few LDC, no global look-up in front
+// of the tile's loads); every CTA runs the per-tensor body of fq_affine_kernel<T, CH_PT> on one 8 KB tile of its site.
+constexpr int kSitesCap = 64;
+struct alignas(16) SiteEntry {
+    const void* x;
+    void* y;
+    int64_t n;
+    float scale;
+    int32_t zp, qmin, qmax;
+    int32_t dtype, pad;
+};
+struct SitesParams {
+    int32_t n_sites, pad[3];
+    int32_t starts[kSitesCap + 4];              // starts[k] = first tile of site k; starts[n_sites] = number of tiles
+    SiteEntry e[kSitesCap];
+};
+static_assert(sizeof(SitesParams) <= 4096, "kernel parameter space");
+
+template <typename T, bool RINT>
+__device__ __forceinline__ void site_tile(const SiteEntry& s, const int64_t tile) {
+    using Op = AffineOp<RINT>;
+    constexpr int UNROLL = 2, V = 16 / sizeof(T), WORDS = 4;
+    constexpr uint32_t TILE = kThreads * UNROLL * V;
+    const uint32_t tid = threadIdx.x;
+    const int64_t t0 = tile * TILE;
+    const int64_t remaining = s.n - t0;
+    const bool full = remaining >= (int64_t)TILE;
+    const T* xt = reinterpret_cast<const T*>(s.x) + t0;
+    T* yt = reinterpret_cast<T*>(s.y) + t0;
+    uint32_t w[UNROLL][WORDS];
+    if (full) {
+#pragma unroll
+        for (int j = 0; j < UNROLL; ++j) ld_words<WORDS>(xt + (size_t)(j * kThreads + tid) * V, w[j]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < UNROLL; ++j) {
+            int64_t l = (int64_t)(j * kThreads + tid) * V;
+            if (l + V <= remaining) ld_words<WORDS>(xt + l, w[j]);
+            else {
+                T tmp[V];
+#pragma unroll
+                for (int e = 0; e < V; ++e) tmp[e] = (l + e < remaining) ? xt[l + e] : from_f32<T>(0.0f);
+                memcpy(w[j], tmp, 16);
+            }
+        }
+    }
+    AffineArgs a;                                   // only the fields AffineOp::make reads
+    a.qmin = s.qmin;
+    a.qmax = s.qmax;
+    const typename Op::ChanParams p = Op::make(s.scale, s.zp, a);
+#pragma unroll
+    for (int j = 0; j < UNROLL; ++j) {
+        const uint32_t l = (uint32_t)(j * kThreads + tid) * V;
+        float f[V];
+        int code;
+        Pack<T, V>::unpack(w[j], f);
+#pragma unroll
+        for (int e = 0; e < V; ++e) f[e] = Op::template apply<false>(f[e], p, code);
+        if (full || (int64_t)l + V <= remaining) {
+            Pack<T, V>::pack(f, w[j]);
+            st_words<WORDS>(yt + l, w[j]);
+        } else if ((int64_t)l < remaining) {
+            const int cnt = (int)(remaining - l);
+            for (int e = 0; e < V; ++e)
+                if (e < cnt) yt[l + e] = from_f32<T>(f[e]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) fq_affine_sites_kernel(const __grid_constant__ SitesParams p) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int tile = blockIdx.x;
+    int lo = 0, hi = p.n_sites;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (p.starts[mid] <= tile) lo = mid; else hi = mid;
+    }
+    const SiteEntry& s = p.e[lo];
+    const int64_t t = (int64_t)(tile - p.starts[lo]);
+    const bool fast = (int64_t)s.qmax - s.qmin < kFastRangeLimit;
+    if (s.dtype == MCTQ_F32) { if (fast) site_tile<float, false>(s, t); else site_tile<float, true>(s, t); }
+    else if (s.dtype == MCTQ_BF16) { if (fast) site_tile<__nv_bfloat16, false>(s, t); else site_tile<__nv_bfloat16, true>(s, t); }
+    else { if (fast) site_tile<__half, false>(s, t); else site_tile<__half, true>(s, t); }
+}
+
 }  // namespace mctq
 
 using namespace mctq;
@@ -876,6 +965,43 @@ int mctq_fq_affine_multi(const MctqTensorDesc* descs_dev, const int32_t* tile_st
     if (!descs_dev || !tile_starts_dev || n_desc < 1 || total_tiles < 0 || total_tiles > 0x7fffffffLL) return MCTQ_E_BADARG;
     if (total_tiles == 0) return 0;
     return launch_streaming(fq_affine_multi_kernel, (unsigned)total_tiles, 0, (cudaStream_t)stream, descs_dev, tile_starts_dev, n_desc);
+}
+
+int mctq_fq_affine_scalar_multi(const MctqSiteDesc* sites, int n_sites, void* stream) {
+    if (n_sites < 0 || (n_sites > 0 && !sites)) return MCTQ_E_BADARG;
+    for (int k = 0; k < n_sites; ++k) {                     // validate everything before anything is launched
+        const MctqSiteDesc& d = sites[k];
+        if (d.n < 0 || (d.n > 0 && (!d.x || !d.y))) return MCTQ_E_BADARG;
+        if (d.dtype != MCTQ_F32 && d.dtype != MCTQ_BF16 && d.dtype != MCTQ_F16) return MCTQ_E_DTYPE;
+        if (d.qmin > d.qmax) return MCTQ_E_RANGE;
+        if (d.n > 0 && (!aligned16(d.x) || !aligned16(d.y))) return MCTQ_E_BADARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    SitesParams p;
+    int k = 0;
+    while (k < n_sites) {
+        memset(&p, 0, sizeof(p));
+        int64_t tiles = 0;
+        int m = 0;
+        for (; k < n_sites && m < kSitesCap; ++k) {
+            const MctqSiteDesc& d = sites[k];
+            if (d.n == 0) continue;
+            const int64_t tile_elems = (int64_t)kThreads * 2 * (d.dtype == MCTQ_F32 ? 4 : 8);
+            const int64_t t = (d.n + tile_elems - 1) / tile_elems;
+            if (tiles + t > 0x7fffffffLL) { if (m == 0) return MCTQ_E_BADARG; break; }       // next launch takes it
+            SiteEntry& e = p.e[m];
+            e.x = d.x; e.y = d.y; e.n = d.n; e.scale = d.scale; e.zp = d.zp; e.qmin = d.qmin; e.qmax = d.qmax; e.dtype = d.dtype;
+            p.starts[m] = (int32_t)tiles;
+            tiles += t;
+            ++m;
+        }
+        if (m == 0) continue;
+        p.n_sites = m;
+        p.starts[m] = (int32_t)tiles;
+        int rc = launch_streaming(fq_affine_sites_kernel, (unsigned)tiles, 0, st, p);
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 }  // extern "C"

@@ -248,7 +248,12 @@ __device__ __forceinline__ void locate(uint32_t l, const Window& w, const Args& 
 // launch carries no programmatic dependency) and pdl_launch_dependents(), which lets the NEXT kernel of the stream be
 // scheduled while this one is still running: its CTAs take the SM slots that free up during our tail.
 //
-// Two orders exist, selected per launch by the host (`early` in the kernel arguments, see pdl_plan_launch):
+// Two orders exist, selected per launch by the host (`early` in the kernel arguments, see pdl_plan_launch).  The early
+// order is OPT-IN (mctq_set_tuning key 3 = 2; Python: `with mct_quantizers_b200.private_stream():`): the library cannot see
+// kernels other libraries enqueue between two of its launches, and such a kernel may itself trigger its dependents before
+// it has stored its results (cuDNN / CUTLASS kernels do), so loads in front of the wait are only legal when the caller
+// guarantees that nothing else feeds these launches on the stream.  Measured on the MobileNetV2 step: +1.6 % (6656 ->
+// 6761 GB/s); an L2-prefetch-before-the-wait variant that would be legal unconditionally gained nothing (6647) and was dropped.
 //   late  : wait -> trigger -> loads -> math -> stores     the dependent CTAs sit idle in their wait during our tail
 //   early : loads -> wait -> trigger -> math -> stores     the dependent CTAs already have their tile in flight while
 //           our last wave drains: back-to-back launches (54 per MobileNetV2 step, 96 per Llama-7B weight pass) keep the
@@ -265,7 +270,7 @@ __device__ __forceinline__ void pdl_gate(bool now) { if (now) { pdl_wait(); pdl_
 // trigger, so the dependent kernel cannot start before it completes and the order is irrelevant.  Launches whose outputs
 // are not described (multi-tensor plans) record "unknown", which forces the late order on their successor.
 struct IoSpan { const void* p; size_t bytes; };
-int pdl_plan_launch(cudaStream_t st, const IoSpan* in, int n_in, const IoSpan* out, int n_out);   // 1 = early order is safe
+int pdl_plan_launch(cudaStream_t st, const IoSpan* in, int n_in, const IoSpan* out, int n_out);   // 1 = early order allowed
 
 // ------------------------------------------------------------------------------------------ TMA bulk staging
 // Parameter tables that are already laid out in global memory the way a CTA wants them in shared memory (prepared LUT

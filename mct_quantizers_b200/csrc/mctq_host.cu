@@ -9,7 +9,7 @@ std::atomic<int64_t> g_launches{0};
 int g_unroll = 0;           // 0 = automatic (per-tensor tiles: 2 vectors per thread, per-channel tiles: 4)
 int g_force_rint = 0;
 int g_force_ieee_div = 0;
-int g_pdl = 2;              // 0 off, 1 programmatic dependent launch (wait first), 2 + loads before the wait when provably safe
+int g_pdl = 1;              // 0 off, 1 programmatic dependent launch (wait first), 2 (opt-in) + loads before the wait when the input is not the previous launch's output
 int g_lut_shfl = 1;
 int g_wide = 1;             // 8-element vectors / 256-bit stores where a kernel has them (key 5)
 int g_multi_span = 4;       // tiles per CTA in the multi-tensor LUT launch: 1 or 4 (key 6; read when a plan is compiled)

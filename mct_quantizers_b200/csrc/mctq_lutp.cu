@@ -167,8 +167,10 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
 // V: elements per vector.  4 everywhere (8-byte loads of 2-byte types, one 16-byte f32 store), or 8 for 2-byte types when
 // the whole vector lies in one channel (CH_PT, CH_VEC with rows that are a multiple of 8): one 16-byte load, one 32-byte
 // store (STG.256), half the per-vector bookkeeping per element -- the 2-byte kernels are instruction-issue bound, not HBM bound.
+// `phase`: how many tiles this CTA has already staged through sm_bar.  The mbarrier is initialised ONCE per CTA (phase 0)
+// and re-armed for every further tile; its parity alternates with the phase (re-initialising a live mbarrier is undefined).
 template <typename T, int CHMODE, int CODE, int UNROLL, int V>
-__device__ __forceinline__ void lutp_tile(const LutPArgs& a, const int64_t tile_index) {
+__device__ __forceinline__ void lutp_tile(const LutPArgs& a, const int64_t tile_index, const uint32_t phase = 0) {
     constexpr int WORDS_IN = V * sizeof(T) / 4;
     constexpr uint32_t TILE = kThreads * UNROLL * V;
     static_assert(V == 4 || (V == 8 && sizeof(T) == 2 && CHMODE != CH_ELEM), "vector width");
@@ -181,8 +183,10 @@ __device__ __forceinline__ void lutp_tile(const LutPArgs& a, const int64_t tile_
     const int64_t remaining = a.n - t0;
     const bool full = remaining >= (int64_t)TILE;
     const T* xt = reinterpret_cast<const T*>(a.x) + t0;
-    pdl_wait();
-    pdl_launch_dependents();
+    if (phase == 0) {
+        pdl_wait();
+        pdl_launch_dependents();
+    }
 
     uint32_t w[UNROLL][WORDS_IN];
     if (full) {
@@ -212,7 +216,7 @@ __device__ __forceinline__ void lutp_tile(const LutPArgs& a, const int64_t tile_
     uint8_t* sm_cells = reinterpret_cast<uint8_t*>(sm_cq) + (a.off_cells - a.off_cq);
     uint8_t* sm_orig = sm_cells + ((a.NC + 1 + 15) & ~15);
     if (tid == 0) {
-        mbar_init(&sm_bar, 1);
+        if (phase == 0) mbar_init(&sm_bar, 1);
         uint32_t c0 = 0;
         if (CHMODE != CH_PT) {
             const int64_t g0 = a.elem_offset + t0;
@@ -236,7 +240,7 @@ __device__ __forceinline__ void lutp_tile(const LutPArgs& a, const int64_t tile_
     __syncthreads();                                                  // barrier init + window visible to everyone
     Window win;
     if (CHMODE != CH_PT) win = sm_win;
-    mbar_wait(&sm_bar, 0);
+    mbar_wait(&sm_bar, phase & 1u);
 
     // Everything below addresses shared memory through 32-bit shared-window addresses: the element loop is
     //   u = sat(x * s' + 0.5); cell = low bits of fma(u, NC, 1.5 * 2^23); b = cells[cell]          (candidate threshold)
@@ -407,8 +411,8 @@ __device__ __forceinline__ void lutp_span(const LutPArgs& a, int64_t span) {
 #pragma unroll 1
     for (int g = 0; g < SPAN; ++g) {
         if (g && (first + g) * TILE >= a.n) break;
-        if (g) __syncthreads();                  // everybody is done with the staged tables / the mbarrier of the previous tile
-        lutp_tile<T, CHMODE, MCTQ_CODES_NONE, 4, V>(a, first + g);
+        if (g) __syncthreads();                  // everybody is done with the staged tables and has left the previous phase's wait
+        lutp_tile<T, CHMODE, MCTQ_CODES_NONE, 4, V>(a, first + g, (uint32_t)g);
     }
 }
 

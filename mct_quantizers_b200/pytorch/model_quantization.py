@@ -9,7 +9,7 @@ from typing import Dict, List
 
 import torch
 
-from mct_quantizers_b200.ops import MultiTensorPlan, LutMultiPlan
+from mct_quantizers_b200.ops import MultiTensorPlan, LutMultiPlan, ScalarSitesPlan
 
 
 def _is_affine_weight_quantizer(q) -> bool:
@@ -38,16 +38,17 @@ def plan_for(weight_vars) -> "WeightPlan":
     return WeightPlan(weight_vars)
 
 
-def _signature(w, q):
-    """What a plan captured of one (weight, quantizer) pair: storage, placement and layout of the weight plus the identity and
-    in-place version of the quantizer's parameter tensors.  A plan whose signatures no longer match the live objects
-    (model.to(), .half(), load_state_dict into new storage, a re-assigned parameter, edited thresholds) is rebuilt."""
-    sig = [w.data_ptr(), w.device, w.dtype, tuple(w.shape), tuple(w.stride())]
-    for name in ('scales', 'zero_points', '_threshold_torch'):
-        t = q.__dict__.get(name)
-        if isinstance(t, torch.Tensor):
-            sig += [t.data_ptr(), -1 if t.is_inference() else t._version]
-    return tuple(sig)
+_PARAM_NAMES = ('scales', 'zero_points', '_threshold_torch')
+
+
+def _live_signature(ws, params, qs):
+    """What a plan captured of its (weight, quantizer) pairs: storage, placement and layout of every weight, identity and
+    in-place version of the quantizers' parameter tensors, the reuse flags.  A plan whose signature no longer matches the
+    live objects (model.to(), .half(), load_state_dict into new storage, a re-assigned parameter, edited thresholds) is
+    rebuilt.  Flat comprehensions: ~1 us per tensor."""
+    return ([(w.data_ptr(), w.dtype, w.shape, w.stride()) for w in ws],
+            [(t.data_ptr(), -1 if t.is_inference() else t._version) for t in params],
+            [(getattr(q, 'enable_reuse', False), id(q.__dict__.get('scales')), id(q.__dict__.get('_threshold_torch'))) for q in qs])
 
 
 class WeightPlan:
@@ -99,7 +100,10 @@ class WeightPlan:
             self._plans.append((idx, MultiTensorPlan(items)))
         for dev, (idx, items) in lut_by_dev.items():
             self._lut_plans.append((idx, LutMultiPlan(items)))
-        self._sigs = [_signature(w, q) + (bool(q.__dict__.get('enable_reuse', False)),) for _, w, q in self.vars]
+        self._ws = [w for _, w, _ in self.vars]
+        self._qs = [q for _, _, q in self.vars]
+        self._params = [t for q in self._qs for t in (q.__dict__.get(n) for n in _PARAM_NAMES) if isinstance(t, torch.Tensor)]
+        self._sigs = _live_signature(self._ws, self._params, self._qs)
 
     # first plan of each family (single-device models: the only one)
     @property
@@ -111,11 +115,11 @@ class WeightPlan:
         return self._lut_plans[0][1] if self._lut_plans else None
 
     def stale(self) -> bool:
-        return any(_signature(w, q) + (bool(q.__dict__.get('enable_reuse', False)),) != sig
-                   for (_, w, q), sig in zip(self.vars, self._sigs))
+        return _live_signature(self._ws, self._params, self._qs) != self._sigs
 
-    def run(self) -> List[torch.Tensor]:
-        if self.stale():
+    def run(self, validate: bool = True) -> List[torch.Tensor]:
+        """`validate=False` skips the staleness check (for callers that own the weights and know nothing moved)."""
+        if validate and self.stale():
             self._build()
         out = [None] * self.n
         for idx, plan in self._plans:
@@ -127,6 +131,74 @@ class WeightPlan:
         for k, w, q in self.other:
             out[k] = q(w)
         return out
+
+
+class ActivationPlan:
+    """Launch plan over (holder or activation quantizer, tensor) pairs whose inputs ALREADY EXIST: every per-tensor affine
+    site (ActivationSymmetric / POT / Uniform) of a device runs in ONE launch (`ScalarSitesPlan`), any other quantizer
+    (LUT, user-defined), CPU tensor or non-dense view through its own call.  Use it where a model's activations are
+    available together -- calibration / analysis passes over recorded activations, batched post-processing, benchmarks;
+    inside a forward pass each holder still sees its input only after the producing layer ran, so holders keep their
+    per-call path there (or are fused into their producer, fused_activation_holder.py).
+
+        plan = ActivationPlan([(holder_k, x_k) for k in sites])
+        ys = plan.run()            # output buffers are owned by the plan and refreshed by every run()
+
+    run() revalidates what the plan captured (storage pointer, dtype, shape, strides of every input; scale / zero point /
+    range of every quantizer) and rebuilds on any difference.  Results are bit-identical to `holder(x)`."""
+
+    def __init__(self, pairs):
+        self.pairs = [(getattr(h, 'activation_holder_quantizer', h), x) for h, x in pairs]
+        self.n = len(self.pairs)
+        self._build()
+
+    @staticmethod
+    def _params(q):
+        from mct_quantizers_b200.pytorch.fused_activation_holder import affine_scalar_params
+        if q.__dict__.get('_use_custom_impl', False) and torch.jit.is_tracing():
+            return None
+        return affine_scalar_params(q)
+
+    def _sig(self):
+        return [(x.data_ptr(), x.dtype, x.shape, x.stride(), self._params(q)) for q, x in self.pairs]
+
+    def _build(self):
+        self._plans, self.other = [], []
+        by_dev = {}
+        for k, (q, x) in enumerate(self.pairs):
+            prm = self._params(q)
+            if prm is not None and ScalarSitesPlan.accepts(x):
+                idx, items = by_dev.setdefault(x.device, ([], []))
+                idx.append(k)
+                items.append((x.detach(), prm[0], prm[1], prm[2], prm[3]))
+            else:
+                self.other.append((k, q, x))
+        for dev, (idx, items) in by_dev.items():
+            self._plans.append((idx, ScalarSitesPlan(items)))
+        self._sigs = self._sig()
+
+    def run(self) -> List[torch.Tensor]:
+        if self._sig() != self._sigs:
+            self._build()
+        out = [None] * self.n
+        for idx, plan in self._plans:
+            for k, y in zip(idx, plan.run()):
+                out[k] = y
+        for k, q, x in self.other:
+            out[k] = q(x)
+        return out
+
+    def outputs_of(self, k: int) -> torch.Tensor:
+        """The plan-owned output buffer of pair `k` as the last run() left it (None for pairs outside the fused launch)."""
+        for idx, plan in self._plans:
+            if k in idx:
+                return plan.outputs[idx.index(k)]
+        return None
+
+
+def quantize_activations(pairs) -> List[torch.Tensor]:
+    """[holder_k(x_k)] for (holder or quantizer, tensor) pairs, per-tensor affine sites in one launch per device."""
+    return ActivationPlan(pairs).run()
 
 
 def quantize_weight_vars(weight_vars) -> Dict[str, torch.Tensor]:

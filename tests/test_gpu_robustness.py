@@ -152,3 +152,101 @@ def test_fused_holder_wide_range_falls_back(Q):
     x = torch.randn(5000, device=DEV) * 3
     y = fh(x)
     assert torch.equal(y, q(torch.relu(x)))
+
+
+def test_activation_plan_matches_per_holder_calls_and_oracle(Q):
+    """One launch over many per-tensor sites (mctq_fq_affine_scalar_multi) == the holders called one by one == the oracle:
+    mixed dtypes, ragged sizes, a channels_last tensor, more sites than one launch holds (64), a 23-bit range (rint path),
+    a LUT holder and a misaligned view (both fall back to their own call); the plan rebuilds when an input moves."""
+    import mct_quantizers_b200 as mctq
+    rng = np.random.default_rng(3)
+    quants = [Q.ActivationUniformInferableQuantizer(8, [-1.3], [2.9]), Q.ActivationSymmetricInferableQuantizer(8, [3.7], True),
+              Q.ActivationPOTInferableQuantizer(4, [2.0], False), Q.ActivationSymmetricInferableQuantizer(23, [4.0], True)]
+    pairs = []
+    sizes = [1, 7, 2048, 2049, 4097, 70001, 8192 * 3 + 5]
+    for k in range(70):
+        dt = (torch.float32, torch.bfloat16, torch.float16)[k % 3]
+        n = sizes[k % len(sizes)]
+        x = torch.from_numpy((rng.standard_normal(n) * 2).astype(np.float32)).to(dt).to(DEV)
+        pairs.append((mctq.PytorchActivationQuantizationHolder(quants[k % 4]), x))
+    cl = torch.randn(2, 8, 5, 6, device=DEV).contiguous(memory_format=torch.channels_last)
+    pairs.append((quants[0], cl))
+    lut_q = Q.ActivationLutPOTInferableQuantizer(4, [-8.0, -3.0, 0.0, 1.0, 5.0, 7.0], [4.0], True)
+    pairs.append((lut_q, torch.randn(300, device=DEV)))
+    pairs.append((quants[1], torch.randn(1001, device=DEV)[1:]))              # 4-byte aligned view
+    plan = mctq.ActivationPlan(pairs)
+    assert len(plan.other) == 2 and len(plan._plans) == 1 and plan._plans[0][1].n_sites == 71
+    ys = plan.run()
+    torch.cuda.synchronize()
+    for (h, x), y in zip(pairs, ys):
+        want = h(x)
+        assert y.dtype == want.dtype and y.shape == want.shape and y.stride() == want.stride()
+        assert torch.equal(y.view(torch.int32) if y.dtype == torch.float32 else y.view(torch.int16),
+                           want.view(torch.int32) if y.dtype == torch.float32 else want.view(torch.int16))
+    q = quants[0]
+    x, y = pairs[4][1], ys[4]
+    want = oracle.fq_affine(G.from_torch(x), oracle.BF16, np.array([q.scale], np.float64).astype(np.float32),
+                            np.array([q.zero_point], np.int32), 1, 1, 0, 255)
+    assert G.bits_equal(G.from_torch(y), np.asarray(want).reshape(-1))
+    # a moved input: same values in new storage -> rebuilt plan, same result; edited values -> new result
+    old = pairs[5][1]
+    plan.pairs[5] = (plan.pairs[5][0], old.clone() * 0.5)
+    y5 = plan.run()[5]
+    assert torch.equal(y5, pairs[5][0](old * 0.5))
+    assert mctq.quantize_activations(pairs[:3])[2].shape == pairs[2][1].shape
+
+
+def test_activation_plan_c_abi_argument_errors():
+    import ctypes
+    from mct_quantizers_b200 import _native
+    lib = _native.load()
+    x = torch.zeros(64, device=DEV)
+    y = torch.empty_like(x)
+    d = (_native.MctqSiteDesc * 1)()
+    d[0].x, d[0].y, d[0].n, d[0].dtype, d[0].scale, d[0].zp, d[0].qmin, d[0].qmax = x.data_ptr(), y.data_ptr(), 64, 0, 0.5, 0, -128, 127
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert lib.mctq_fq_affine_scalar_multi(ctypes.cast(d, ctypes.c_void_p), 1, st) == 0
+    d[0].dtype = 9
+    assert lib.mctq_fq_affine_scalar_multi(ctypes.cast(d, ctypes.c_void_p), 1, st) == -2
+    d[0].dtype, d[0].qmin = 0, 300
+    assert lib.mctq_fq_affine_scalar_multi(ctypes.cast(d, ctypes.c_void_p), 1, st) == -3
+    d[0].qmin, d[0].x = -128, x.data_ptr() + 4
+    assert lib.mctq_fq_affine_scalar_multi(ctypes.cast(d, ctypes.c_void_p), 1, st) == -1
+    assert lib.mctq_fq_affine_scalar_multi(None, 0, st) == 0
+    torch.cuda.synchronize()
+
+
+def test_private_stream_early_order_keeps_dependent_chains_correct(Q):
+    """Opt-in early order (loads before griddepcontrol.wait): independent back-to-back calls and chains in which every call
+    consumes the previous call's output give the same bits as the default order."""
+    import mct_quantizers_b200 as mctq
+    from mct_quantizers_b200 import _native
+    g = torch.Generator(device=DEV).manual_seed(7)
+    xs = [torch.empty(1 << 22, device=DEV).uniform_(-6, 6, generator=g) for _ in range(6)]
+    qs = [Q.ActivationUniformInferableQuantizer(8, [-1.0 - 0.1 * k], [2.0 + 0.3 * k]) for k in range(6)]
+
+    def chain():
+        outs = []
+        for x in xs:                                   # independent inputs (early order applies) ...
+            y = x
+            for q in qs:                               # ... each followed by a chain: input = previous output (late order)
+                y = q(y)
+            outs.append(y)
+        fh = mctq.PytorchFusedActivationQuantizationHolder(qs[0], "add_relu")
+        outs.append(fh(outs[0], outs[1]))
+        return outs
+
+    want = chain()
+    torch.cuda.synchronize()
+    with mctq.private_stream():
+        assert _native.load().mctq_set_tuning(3, 2) == 2
+        got = chain()
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):                     # a stream the library has not seen: first launch falls back to the late order
+            s.wait_stream(torch.cuda.current_stream())
+            got2 = chain()
+        s.synchronize()
+    assert _native.load().mctq_set_tuning(3, 1) == 1   # restored on exit
+    torch.cuda.synchronize()
+    for a, b, c in zip(want, got, got2):
+        assert torch.equal(a, b) and torch.equal(a, c)
