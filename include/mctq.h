@@ -229,7 +229,9 @@ int mctq_fq_lut_prepared(const void* x, float* y, void* idx, int64_t n, int x_dt
  * mctq_lut_multi_plan compiles the HOST descriptor array into an opaque plan blob of
  * mctq_lut_multi_plan_bytes(descs, n_desc) bytes in HOST memory (returns the number of CTAs of the launch, or < 0:
  * MCTQ_E_RANGE / MCTQ_E_BADARG mean "this tensor needs the single-tensor / generic entry point").  The launch passes the
- * per-tensor argument blocks as kernel parameters (one launch per 180 tensors), so there is no device-side copy of the plan.
+ * per-tensor argument blocks as kernel parameters, so there is no device-side copy of the plan; the tensors are grouped by
+ * kernel variant (dtype, channel mode, vector width, record kind) and every group runs as launches of <= 64 tensors, each
+ * specialised for its variant (a model whose LUT weights share one layout is one launch per 64 tensors).
  * x, y and the prepared blobs must stay valid while the plan is in use. */
 typedef struct MctqLutTensorDesc {
     const void* x;            /* device, dtype below, 16-byte aligned */
@@ -284,7 +286,8 @@ int64_t mctq_launch_count(void);
  *   their stores are visible); opt-in, see mct_quantizers_b200.private_stream(),
  * key 4 = warp-shuffle search in the generic LUT kernel for tables of <= 32 entries (default 1),
  * key 5 = wide vectors (8 elements per vector, 256-bit stores) in the kernels that have them (default 1),
- * key 6 = tiles per CTA of the multi-tensor LUT launch, 1 or 4 (default 4; read by mctq_lut_multi_plan);
+ * key 6 = (retired: the multi-tensor LUT launches run one tile per CTA; the key is accepted and ignored),
+ * key 7 = xy-record variant of the prepared LUT kernel for per-tensor / long-row launches (default 1);
  * returns previous value or <0 */
 int mctq_set_tuning(int key, int value);
 /* device self-test of the 5-op correctly-rounded division used by the LUT kernels against __fdiv_rn

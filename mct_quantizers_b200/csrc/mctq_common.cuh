@@ -32,6 +32,7 @@ extern int g_force_ieee_div;
 extern int g_lut_shfl;      // warp-shuffle search in the generic LUT kernel for tables of <= 32 entries (key 4)
 extern int g_wide;          // wide (8-element / 256-bit) vector variants (mctq_set_tuning key 5)
 extern int g_multi_span;    // tiles per CTA of the multi-tensor LUT launch (mctq_set_tuning key 6)
+extern int g_lut_xy;        // xy-record variant of the prepared LUT kernel where it applies (mctq_set_tuning key 7)
 extern int g_pdl;           // programmatic dependent launch for the streaming kernels (mctq_set_tuning key 3)
 
 enum ChMode { CH_PT = 0, CH_VEC = 1, CH_ELEM = 2, CH_LAST = 3 };
@@ -303,9 +304,9 @@ inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? 0 : (int)e; }
 
 // launch with the programmatic-serialization attribute; the caller has already declared the launch to pdl_plan_launch
 template <typename... KArgs, typename... Args>
-inline int launch_planned(void (*kernel)(KArgs...), unsigned grid, size_t smem, cudaStream_t st, Args&&... args) {
+inline int launch_planned(void (*kernel)(KArgs...), dim3 grid, size_t smem, cudaStream_t st, Args&&... args) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
+    cfg.gridDim = grid;
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
@@ -321,7 +322,7 @@ inline int launch_planned(void (*kernel)(KArgs...), unsigned grid, size_t smem, 
 
 // same, for kernels that always use the late order: their outputs are recorded as "unknown"
 template <typename... KArgs, typename... Args>
-inline int launch_streaming(void (*kernel)(KArgs...), unsigned grid, size_t smem, cudaStream_t st, Args&&... args) {
+inline int launch_streaming(void (*kernel)(KArgs...), dim3 grid, size_t smem, cudaStream_t st, Args&&... args) {
     pdl_plan_launch(st, nullptr, 0, nullptr, 0);
     return launch_planned(kernel, grid, smem, st, std::forward<Args>(args)...);
 }

@@ -12,6 +12,7 @@ int g_force_ieee_div = 0;
 int g_pdl = 1;              // 0 off, 1 programmatic dependent launch (wait first), 2 (opt-in) + loads before the wait when the input is not the previous launch's output
 int g_lut_shfl = 1;
 int g_wide = 1;             // 8-element vectors / 256-bit stores where a kernel has them (key 5)
+int g_lut_xy = 1;           // key 7
 int g_multi_span = 4;       // tiles per CTA in the multi-tensor LUT launch: 1 or 4 (key 6; read when a plan is compiled)
 
 // ---- early-order bookkeeping (see mctq_common.cuh): what did the last streaming launch on (device, stream) write?
@@ -88,6 +89,7 @@ int mctq_set_tuning(int key, int value) {
         case 3: prev = g_pdl; if (value < 0 || value > 2) return MCTQ_E_BADARG; g_pdl = value; return prev;
         case 4: prev = g_lut_shfl; g_lut_shfl = value ? 1 : 0; return prev;
         case 5: prev = g_wide; if (value < 0 || value > 2) return MCTQ_E_BADARG; g_wide = value; return prev;
+        case 7: prev = g_lut_xy; g_lut_xy = value ? 1 : 0; return prev;
         case 6: prev = g_multi_span; if (value != 1 && value != 4) return MCTQ_E_BADARG; g_multi_span = value; return prev;
         default: return MCTQ_E_BADARG;
     }

@@ -983,7 +983,8 @@ class LutMultiPlan:
     Build once from [(x, table, K, threshold, per_channel, axis, eps)] (all CUDA, one device; `table` is the host search
     table of the quantizer): every tensor's decision tables are prepared (or taken from the per-quantizer cache), outputs
     are allocated here and reused by every run(); the plan travels as kernel parameters.  run() enqueues ONE kernel
-    (per 180 tensors) on the current stream -- no launch gaps and no per-launch tails between the tensors (Llama-7B: 96 launches -> 1).
+    per kernel variant and 64 tensors on the current stream -- no launch gaps and no per-launch tails between the tensors
+    (Llama-7B: 96 launches -> 2).
     `accepts(item)` tells whether a tensor can be part of a plan (prepared path available, dense, aligned)."""
 
     @staticmethod
@@ -1055,6 +1056,7 @@ class LutMultiPlan:
             raise MctqError(f"mctq_lut_multi_plan: {total}")
         self.total_tiles = int(total)
         self.n_desc = len(items)
+        self.n_launches = int(np.frombuffer(bytes(self._plan_host[:16]), dtype=np.int32)[2])    # one per kernel variant and 64 tensors
 
     def run(self):
         lib = _native.load()

@@ -653,7 +653,14 @@ def test_whole_model_lut_single_launch(Q, lib):
     assert plan.lut_plan is not None and plan.lut_plan.n_desc == len(specs) and plan.plan is not None and not plan.other
     before = lib.mctq_launch_count()
     outs = plan.run()
-    assert lib.mctq_launch_count() - before == 2            # one affine launch + one LUT launch
+    # one affine launch + one LUT launch per kernel variant (this table is deliberately mixed: 7 variants for 8 tensors)
+    assert lib.mctq_launch_count() - before == 1 + plan.lut_plan.n_launches and plan.lut_plan.n_launches <= 7
+    same = [(f"s{k}", torch.randn(16 + k, 520, device=DEV) * 0.05) for k in range(5)]        # one variant -> ONE launch
+    plan_same = WeightPlan([(n, w, Q.WeightsLUTSymmetricInferableQuantizer(4, lut16, [float(v) + 1e-3 for v in w.abs().amax(1)], True, 0, 2))
+                            for n, w in same])
+    before = lib.mctq_launch_count()
+    plan_same.run()
+    assert lib.mctq_launch_count() - before == 1 and plan_same.lut_plan.n_launches == 1
     for (name, w, q), y in zip(triples, outs):
         want = q(w.clone())
         assert y.dtype == want.dtype and y.shape == want.shape and torch.equal(y, want), name
@@ -673,7 +680,7 @@ def test_whole_model_lut_single_launch(Q, lib):
 
 
 def test_weight_plan_under_cuda_graph(Q, lib):
-    """WeightPlan.run() (one affine + one LUT multi-tensor launch; the LUT plan travels as 27 KB of kernel parameters) can be
+    """WeightPlan.run() (one affine launch + one LUT launch per kernel variant; the LUT plans travel as kernel parameters) can be
     captured in a CUDA graph; a replay re-quantizes the CURRENT contents of the weights into the same output buffers."""
     from mct_quantizers_b200.pytorch.model_quantization import WeightPlan
     rng = np.random.default_rng(8)

@@ -285,8 +285,9 @@ def test_multi_plan_host_helper():
 
 
 def test_lut_multi_plan_host_compiler():
-    """mctq_lut_multi_plan is host-only code: descriptor validation, variant selection per tensor, span counts and the
-    180-tensors-per-launch chunking can be checked without a GPU (device pointers are never dereferenced here)."""
+    """mctq_lut_multi_plan is host-only code: descriptor validation, variant selection per tensor, tile counts, the grouping by
+    kernel variant and the 64-tensors-per-launch chunking can be checked without a GPU (device pointers are never
+    dereferenced here)."""
     lib = _native.load()
     assert ctypes.sizeof(_native.MctqLutTensorDesc) == 64
 
@@ -304,17 +305,20 @@ def test_lut_multi_plan_host_compiler():
         buf = (ctypes.c_uint8 * nb)()
         return nb, lib.mctq_lut_multi_plan(ctypes.cast(arr, ctypes.c_void_p), len(ds), ctypes.cast(buf, ctypes.c_void_p), nb), buf
 
-    span_f32 = 256 * 4 * 4 * 4            # threads x unroll x 4-element vectors x 4 tiles per CTA
-    span_bf16_wide = 256 * 4 * 8 * 4      # 2-byte inputs, rows a multiple of 8: 8-element vectors
-    nb, total, buf = plan([desc(span_f32 * 3 + 1, 128, 4096), desc(5, 1, 1), desc(span_bf16_wide * 2, 64, 4096, dtype=1),
-                           desc(span_f32 + 1, 64, 36, dtype=1)])       # rows of 36: not a multiple of 8 -> 4-element vectors
+    tile_f32 = 256 * 4 * 4                # threads x unroll x 4-element vectors, one tile per CTA
+    tile_bf16_wide = 256 * 4 * 8          # 2-byte inputs, rows a multiple of 8: 8-element vectors
+    nb, total, buf = plan([desc(tile_f32 * 3 + 1, 128, 4096), desc(5, 1, 1), desc(tile_bf16_wide * 2, 64, 4096, dtype=1),
+                           desc(tile_f32 + 1, 64, 36, dtype=1)])       # rows of 36: not a multiple of 8 -> 4-element vectors
     assert total == 4 + 1 + 2 + 2 and nb > 64
     hdr = np.frombuffer(bytes(buf)[:32], dtype=np.int32)
-    assert hdr[1] == 4 and hdr[2] == 1 and hdr[3] == 4                 # n_desc, one launch, 4 tiles per CTA
-    # more than 180 tensors: several launches, every one with its own tile numbering
+    assert hdr[1] == 4 and hdr[2] == 4 and hdr[3] == 1                 # n_desc, four kernel variants = four launches, 1 tile per CTA
+    # tensors of one variant share a launch
+    _, total1, buf1 = plan([desc(tile_f32 * 2, 16, 4096), desc(tile_f32 * 5, 16, 8192), desc(tile_f32, 16, 4096)])
+    assert total1 == 8 and np.frombuffer(bytes(buf1)[:32], dtype=np.int32)[2] == 1
+    # more than 64 tensors of one variant: several launches, every one with its own tile numbering
     nb2, total2, buf2 = plan([desc(1000 + k, 8, 128) for k in range(400)])
-    assert total2 == 400 and np.frombuffer(bytes(buf2)[:32], dtype=np.int32)[2] == 3
-    assert nb2 > 2 * nb
+    assert total2 == 400 and np.frombuffer(bytes(buf2)[:32], dtype=np.int32)[2] == 7
+    assert nb2 > nb
     # tensors the prepared path cannot run are refused (the caller keeps them on their own call)
     assert plan([desc(100, 4, 25, x=0x7f0000000004)])[1] == -1         # misaligned x
     assert plan([desc(100, 4, 25, bw=14)])[1] == -3                    # lut_values_bitwidth > 10: cell table too large

@@ -116,6 +116,17 @@ def main():
     mplan = ops.LutMultiPlan(items)
     jobs.append(("lut-prepared multi-tensor launch, 3 Llama-7B matrices (kernel-parameter plan) [bf16]", total * 6, lambda: (mplan.run(), 0)[1], total))
 
+    # all MobileNetV2 activation sites (batch 32) in ONE mctq_fq_affine_scalar_multi launch
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import MBV2_ACTS
+    from mct_quantizers_b200.pytorch import quantizers as Q
+    from mct_quantizers_b200.pytorch.model_quantization import ActivationPlan
+    acts = [torch.empty((32,) + shp, device=dev).normal_(0, 1) for shp in MBV2_ACTS]
+    aplan = ActivationPlan([(Q.ActivationUniformInferableQuantizer(8, [-5.5], [5.7]), x) for x in acts])
+    n_sites = sum(x.numel() for x in acts)
+    jobs.append(("affine per-tensor multi-site launch, 53 MobileNetV2 sites batch 32 (kernel-parameter site table) [f32]", n_sites * 8,
+                 lambda: (aplan.run(), 0)[1], n_sites))
+
     torch.cuda.synchronize()
     for _, _, fn, _ in jobs:          # warm-up (module load, shared-memory attributes) outside the profiled range
         rc = fn()
