@@ -138,7 +138,35 @@ def load(build_if_missing=True):
             if handle.mctq_set_tuning(int(k), int(v)) < 0:
                 raise MctqError(f"MCTQ_TUNE: mctq_set_tuning({k}, {v}) rejected")
         _lib = handle
+        _load_fast()
     return _lib
+
+
+fast = None      # module _mctq_fast (CPython wrappers of the hottest entry points) or None: then every call goes through ctypes
+
+
+def _load_fast():
+    """Import the optional CPython front door after libmctq_sm100.so is mapped (its DT_NEEDED entry then binds to the same
+    instance: one launch counter, one set of tuning switches).  MCTQ_NO_FASTCALL=1 keeps everything on ctypes."""
+    global fast
+    if os.environ.get("MCTQ_NO_FASTCALL"):
+        return
+    try:
+        from mct_quantizers_b200 import build as _build
+        path = _build.pyext_path()
+        if not os.path.exists(path):
+            try:
+                _build.build_pyext()
+            except Exception:
+                return
+        if os.path.exists(path):
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("mct_quantizers_b200._mctq_fast", path)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            fast = mod
+    except Exception:
+        fast = None
 
 
 def check(rc, what):

@@ -17,6 +17,12 @@ SOURCES = ["mctq_affine.cu", "mctq_lut.cu", "mctq_lutp.cu", "mctq_fused.cu", "mc
 OBJ_DIR = os.path.join(HERE, "csrc", "_obj")
 INCLUDE = os.path.join(ROOT, "include")
 LIB = os.path.join(HERE, "libmctq_sm100.so")
+PYEXT_SRC = os.path.join(CSRC, "mctq_pyext.c")
+
+
+def pyext_path():
+    import sysconfig
+    return os.path.join(HERE, "_mctq_fast" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -77,7 +83,27 @@ def build(force=False, verbose=False):
         raise RuntimeError(f"nvcc failed for {failed}")
     if jobs or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
         subprocess.run([nvcc] + LINK_FLAGS + ["-o", LIB] + objs, check=True)
+    build_pyext(force)
     return LIB
+
+
+def build_pyext(force=False):
+    """_mctq_fast: CPython wrappers (METH_FASTCALL) around the hottest entry points of libmctq_sm100.so -- plumbing that takes
+    ~4 us of ctypes argument conversion out of every small call.  Optional: without a C compiler or Python headers the
+    package uses ctypes for every call."""
+    import sysconfig
+    out = pyext_path()
+    inc = sysconfig.get_paths().get("include")
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if not cc or not inc or not os.path.exists(os.path.join(inc, "Python.h")):
+        return None
+    newest = max(os.path.getmtime(PYEXT_SRC), os.path.getmtime(os.path.join(INCLUDE, "mctq.h")))
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= newest:
+        return out
+    cmd = [cc, "-O2", "-shared", "-fPIC", "-I", INCLUDE, "-I", inc, PYEXT_SRC, "-o", out, "-L", HERE, "-l:libmctq_sm100.so",
+           "-Wl,-rpath,$ORIGIN"]
+    subprocess.run(cmd, check=True)
+    return out
 
 
 if __name__ == "__main__":

@@ -264,12 +264,12 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_gate(bool now) { if (now) { pdl_wait(); pdl_launch_dependents(); } }
 
-// Host side of the early order (mctq_host.cu): the library remembers, per (device, stream), the memory ranges its most
-// recent streaming launch WRITES.  A launch may load before the wait iff none of its inputs overlaps those ranges -- then
-// the kernel it may overlap with (the previous launch of this library on the stream, if it is still running) does not
-// produce its input.  Any other predecessor (a torch kernel, a memcpy, a launch without the attribute) has no early
-// trigger, so the dependent kernel cannot start before it completes and the order is irrelevant.  Launches whose outputs
-// are not described (multi-tensor plans) record "unknown", which forces the late order on their successor.
+// Host side of the early order (mctq_host.cu; only consulted when the caller opted in): the library remembers, per
+// (device, stream), the memory ranges its most recent streaming launch WRITES.  A launch may load before the wait iff none
+// of its inputs overlaps those ranges -- then the kernel it may overlap with (the previous launch of this library on the
+// stream, if it is still running) does not produce its input.  Kernels of OTHER libraries enqueued in between are invisible
+// to this bookkeeping, which is why the order is opt-in.  Launches whose outputs are not described (multi-tensor plans)
+// record "unknown", which forces the late order on their successor.
 struct IoSpan { const void* p; size_t bytes; };
 int pdl_plan_launch(cudaStream_t st, const IoSpan* in, int n_in, const IoSpan* out, int n_out);   // 1 = early order allowed
 

@@ -228,8 +228,9 @@ def affine_scalar_direct(x, scale_f32, zero_point, quant_min, quant_max):
         prev = _get_device()
         if prev != dev.index:
             _set_device(dev.index)
-        rc = lib.mctq_fq_affine_scalar(xd.data_ptr(), y.data_ptr(), None, n, tag, scale_f32, zero_point, quant_min, quant_max,
-                                       0, _raw_stream(dev.index))
+        fast = _native.fast                     # CPython front door (METH_FASTCALL) when built; ctypes otherwise -- same entry point
+        rc = (fast.fq_affine_scalar if fast is not None else lib.mctq_fq_affine_scalar)(
+            xd.data_ptr(), y.data_ptr(), None, n, tag, scale_f32, zero_point, quant_min, quant_max, 0, _raw_stream(dev.index))
         if prev != dev.index:
             _set_device(prev)
         if rc:
@@ -269,8 +270,10 @@ def affine_scalar_pre_direct(x, other, pre_op, scale_f32, zero_point, quant_min,
         prev = _get_device()
         if prev != index:
             _set_device(index)
-        rc = lib.mctq_fq_affine_scalar_pre(xd.data_ptr(), od.data_ptr() if od is not None else None, y.data_ptr(), n, tag,
-                                           pre_op, scale_f32, zero_point, quant_min, quant_max, _raw_stream(index))
+        fast = _native.fast
+        rc = (fast.fq_affine_scalar_pre if fast is not None else lib.mctq_fq_affine_scalar_pre)(
+            xd.data_ptr(), od.data_ptr() if od is not None else None, y.data_ptr(), n, tag, pre_op, scale_f32, zero_point,
+            quant_min, quant_max, _raw_stream(index))
         if prev != index:
             _set_device(prev)
         if rc:
@@ -330,13 +333,16 @@ def _affine_prepared(lib, scale, zero_point, index):
 def _launch_affine_params(lib, x_ptr, y_ptr, codes_ptr, n, tag, scale, zero_point, C, inner, quant_min, quant_max, code_mode, index):
     """mctq_fq_affine_prepared for per-channel parameters (C > 1), mctq_fq_affine otherwise.  The caller has made
     `index` the current device."""
+    fast = _native.fast
     if C > 1 and scale.is_contiguous() and zero_point.is_contiguous():
         blob = _affine_prepared(lib, scale, zero_point, index)
         if blob is not None:
-            return lib.mctq_fq_affine_prepared(x_ptr, y_ptr, codes_ptr, n, tag, blob.data_ptr(), C, inner, 0, quant_min, quant_max,
-                                               code_mode, _raw_stream(index)), "mctq_fq_affine_prepared"
-    return lib.mctq_fq_affine(x_ptr, y_ptr, codes_ptr, n, tag, scale.data_ptr(), zero_point.data_ptr(), C, inner, 0,
-                              quant_min, quant_max, code_mode, _raw_stream(index)), "mctq_fq_affine"
+            return (fast.fq_affine_prepared if fast is not None else lib.mctq_fq_affine_prepared)(
+                x_ptr, y_ptr, codes_ptr, n, tag, blob.data_ptr(), C, inner, 0, quant_min, quant_max, code_mode,
+                _raw_stream(index)), "mctq_fq_affine_prepared"
+    return (fast.fq_affine if fast is not None else lib.mctq_fq_affine)(
+        x_ptr, y_ptr, codes_ptr, n, tag, scale.data_ptr(), zero_point.data_ptr(), C, inner, 0, quant_min, quant_max, code_mode,
+        _raw_stream(index)), "mctq_fq_affine"
 
 
 def affine_params_direct(x, scale, zero_point, C, inner, quant_min, quant_max):
@@ -601,8 +607,9 @@ def lut_weights_direct(x, table, K, threshold, per_channel, axis, eps, cache):
                 prev = _get_device()
                 if prev != index:
                     _set_device(index)
-                rc = lib.mctq_fq_lut_prepared(x.data_ptr(), y.data_ptr(), None, x.numel(), tag, blob_ptr, K_, bw, signed, C, inner, 0, 0,
-                                              _raw_stream(index))
+                fast = _native.fast
+                rc = (fast.fq_lut_prepared if fast is not None else lib.mctq_fq_lut_prepared)(
+                    x.data_ptr(), y.data_ptr(), None, x.numel(), tag, blob_ptr, K_, bw, signed, C, inner, 0, 0, _raw_stream(index))
                 if prev != index:
                     _set_device(prev)
                 if rc == 0:
@@ -962,6 +969,7 @@ class ScalarSitesPlan:
             self.outputs.append(y)
         self.n_sites = len(items)
         self._sites_ptr = ctypes.cast(self._sites, c_vp)
+        self._sites_addr = ctypes.addressof(self._sites)
 
     def run(self):
         lib = _native._lib or _native.load()
@@ -969,7 +977,11 @@ class ScalarSitesPlan:
         prev = _get_device()
         if prev != index:
             _set_device(index)
-        rc = lib.mctq_fq_affine_scalar_multi(self._sites_ptr, self.n_sites, _raw_stream(index))
+        fast = _native.fast
+        if fast is not None:
+            rc = fast.fq_affine_scalar_multi(self._sites_addr, self.n_sites, _raw_stream(index))
+        else:
+            rc = lib.mctq_fq_affine_scalar_multi(self._sites_ptr, self.n_sites, _raw_stream(index))
         if prev != index:
             _set_device(prev)
         if rc:

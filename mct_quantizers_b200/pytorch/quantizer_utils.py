@@ -77,6 +77,23 @@ def lut_search_table(lut_values, lut_values_bitwidth: int, signed: bool) -> torc
     return tab
 
 
+def lut_quantizer_export(tensor_data: torch.Tensor, lut_values: torch.Tensor, signed: bool, threshold, lut_values_bitwidth: int,
+                         eps: float, per_channel: bool = None, channel_axis: int = None, input_rank: int = None) -> torch.Tensor:
+    """The LUT fake-quant spelt in elementary torch ops, for `torch.jit` tracing / ONNX export ONLY (the exporter needs
+    ops it knows; the inference path is `lut_quantizer` below = one fused kernel).  Same op sequence as the reference's
+    lut_quantizer + int_quantization_with_threshold (quantizer_utils.py:95-170): normalise by threshold + eps, scale to the
+    2^lut_values_bitwidth grid, clip (no rounding), nearest centroid by argmin of |t - lut|, scale back by the threshold."""
+    if per_channel:
+        view = [1] * input_rank
+        view[channel_axis] = -1
+        threshold = torch.reshape(threshold, view)
+    mult = 2 ** (lut_values_bitwidth - int(signed))
+    lo, hi = (-2 ** (lut_values_bitwidth - 1), 2 ** (lut_values_bitwidth - 1) - 1) if signed else (0, 2 ** lut_values_bitwidth - 1)
+    t = torch.clip((tensor_data / (threshold + eps)) * mult, min=lo, max=hi).unsqueeze(-1)
+    nearest = torch.argmin(torch.abs(t - lut_values.reshape([1] * (t.dim() - 1) + [-1])), dim=-1)
+    return (lut_values.flatten()[nearest] / mult) * threshold
+
+
 def lut_quantizer(tensor_data: torch.Tensor,
                   lut_values: torch.Tensor,
                   signed: bool,

@@ -8,7 +8,7 @@ from mct_quantizers_b200 import ops  # noqa: F401
 from mct_quantizers_b200.common.base_inferable_quantizer import mark_quantizer, QuantizationTarget, QuantizerID
 from mct_quantizers_b200.common.constants import LUT_VALUES_BITWIDTH, EPS
 from mct_quantizers_b200.common.quant_info import QuantizationMethod
-from mct_quantizers_b200.pytorch.quantizer_utils import to_torch_tensor, get_working_device, lut_quantizer, \
+from mct_quantizers_b200.pytorch.quantizer_utils import to_torch_tensor, get_working_device, lut_quantizer, lut_quantizer_export, \
     lut_search_table
 from mct_quantizers_b200.pytorch.quantizers.base_lut_symmetric_inferable_quantizer import \
     BaseLUTSymmetricInferableQuantizer
@@ -34,6 +34,11 @@ class ActivationLutPOTInferableQuantizer(BaseLUTSymmetricInferableQuantizer):
         self._search_table = None
 
     def __call__(self, inputs: torch.Tensor):
+        if self._use_custom_impl and torch.jit.is_tracing():
+            # export: the reference has no autograd Function for this quantizer -- it traces into the elementary ops of
+            # lut_quantizer (activation_lut_pot_inferable_quantizer.py:76-91), and so does this branch
+            return lut_quantizer_export(inputs, lut_values=self.lut_values.to(inputs.device), signed=self.signed, threshold=self.threshold,
+                                        lut_values_bitwidth=self.lut_values_bitwidth, eps=self.eps)
         if self.__dict__.get('_search_table') is None:     # also absent in objects unpickled from the reference
             self._search_table = lut_search_table(self._lut_values_np, self.lut_values_bitwidth, self.signed)
         # the table stays on the host: the operator keeps per-device copies and the prepared per-channel decision

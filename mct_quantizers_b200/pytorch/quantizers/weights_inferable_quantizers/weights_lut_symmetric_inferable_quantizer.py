@@ -9,7 +9,7 @@ from mct_quantizers_b200 import ops  # noqa: F401
 from mct_quantizers_b200.common.base_inferable_quantizer import mark_quantizer, QuantizationTarget, QuantizerID
 from mct_quantizers_b200.common.constants import LUT_VALUES_BITWIDTH, EPS, ONNX_CUSTOM_OP_DOMAIN
 from mct_quantizers_b200.common.quant_info import QuantizationMethod
-from mct_quantizers_b200.pytorch.quantizer_utils import to_torch_tensor, get_working_device, lut_quantizer, \
+from mct_quantizers_b200.pytorch.quantizer_utils import to_torch_tensor, get_working_device, lut_quantizer, lut_quantizer_export, \
     lut_search_table
 from mct_quantizers_b200.pytorch.quantizers.base_lut_symmetric_inferable_quantizer import \
     BaseLUTSymmetricInferableQuantizer
@@ -80,8 +80,8 @@ class WeightsLUTSymmetricInferableQuantizer(BaseLUTSymmetricInferableQuantizer):
 def _lut_export_forward(input_tensor, lut_values, threshold, lut_values_bitwidth, eps, per_channel, channel_axis, input_rank):
     thr = torch.from_numpy(np.asarray(threshold).astype(np.float32)).to(input_tensor.device)
     lut = torch.from_numpy(np.asarray(lut_values).astype(np.float32)).to(input_tensor.device)
-    return lut_quantizer(input_tensor, lut_values=lut, signed=True, threshold=thr, lut_values_bitwidth=lut_values_bitwidth,
-                         eps=eps, per_channel=per_channel, channel_axis=channel_axis, input_rank=input_rank)
+    return lut_quantizer_export(input_tensor, lut_values=lut, signed=True, threshold=thr, lut_values_bitwidth=lut_values_bitwidth,
+                                eps=eps, per_channel=per_channel, channel_axis=channel_axis, input_rank=input_rank)
 
 
 def _lut_export_symbolic(op_name, cls, g, input_tensor, num_bits, lut_values, threshold, lut_values_bitwidth, eps,
