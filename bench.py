@@ -581,6 +581,32 @@ def run_b200(args):
                "per_call_sync_value": round(n_e2e * BYTES_PER_ELEM / dt_sync / 1e9, 3),
                "path": "with host_pipeline(): quantizer(cpu_pinned_tensor) x 106 -> mctq_fq_affine_host: chunked H2D / kernel / "
                        "D2H on 3 streams, one wait at block exit (per_call_sync_value: the same calls outside the block, this rank)"}
+        # the host link's own ceiling, measured the same way on every rank at once: pinned H2D and D2H copies running together
+        # (what the e2e value can reach at most, in algorithmic bytes: one byte up + one byte down per 2 algorithmic bytes)
+        probe_n = min(128 << 20, host_acts[3].numel())
+        p_in, p_out = host_acts[3].reshape(-1)[:probe_n], torch.empty(probe_n, dtype=torch.float32, pin_memory=True)
+        d_a, d_b = torch.empty(probe_n, device=dev), torch.empty(probe_n, device=dev)
+        sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def link_both():
+            with torch.cuda.stream(sa):
+                d_a.copy_(p_in, non_blocking=True)
+            with torch.cuda.stream(sb):
+                p_out.copy_(d_b, non_blocking=True)
+        link_both()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            link_both()
+        torch.cuda.synchronize()
+        tl = torch.tensor([(time.perf_counter() - t0) / 3], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+        link_gbs = 2 * p_in.numel() * 4 * world / tl.item() / 1e9
+        e2e["host_link_ceiling"] = round(link_gbs, 1)
+        e2e["frac_of_host_link"] = round(e2e["value"] / link_gbs, 3)
+        e2e["host_link_how"] = "pinned H2D + D2H copies of 512 MB running together on every rank, aggregate GB/s (max over ranks)"
+        del p_out, d_a, d_b
         # the host-buffer path must give the device path's bits (same inputs: host_acts are copies of acts)
         if sharding.checksum64(res) != sharding.checksum64(last[:e2e_batch]):
             raise RuntimeError("e2e (host-buffer) result differs from the device-resident result")

@@ -281,9 +281,11 @@ int mctq_fq_lut_host(const void* x_host, float* y_host, int64_t n, int x_dtype,
 int64_t mctq_launch_count(void);
 /* variant selection for experiments: key 0 = unroll (0 = automatic [default], 2, 4, 8), key 1 = force rint path (0/1),
  * key 2 = force IEEE-division LUT path (0/1), key 3 = programmatic dependent launch: 0 off, 1 wait-then-load (default),
- *   2 = load-then-wait for launches whose input is not an output of this library's previous launch on the stream -- only
- *   legal while NO other library's kernels feed these launches on that stream (they may release their dependents before
- *   their stores are visible); opt-in, see mct_quantizers_b200.private_stream(),
+ *   2 = load-then-wait for launches whose input is not an output of a launch of this library still in flight on the stream,
+ *   3 = additionally no wait at all (until a CTA's last instruction) for launches whose buffers are disjoint from those of
+ *   every launch still in flight -- 2 and 3 are only legal while the stream carries NO work of other libraries (their
+ *   kernels may release dependents before their stores are visible; the allocator may recycle their buffers); opt-in, see
+ *   mct_quantizers_b200.private_stream(); changing the key makes the next launch on every stream a waiting one,
  * key 4 = warp-shuffle search in the generic LUT kernel for tables of <= 32 entries (default 1),
  * key 5 = wide vectors (8 elements per vector, 256-bit stores) in the kernels that have them (default 1),
  * key 6 = (retired: the multi-tensor LUT launches run one tile per CTA; the key is accepted and ignored),

@@ -31,7 +31,7 @@ struct AffineArgs {
     const float* prep_soa;
     const int32_t* prep_flags;   // [0] != 0: some zero point is non-zero
     int64_t C4;
-    uint32_t early;              // loads before griddepcontrol.wait (opt-in; pdl_plan_launch found the input is not the predecessor's output)
+    uint32_t early;              // dependent-launch order: 0 late, 1 early, 2 free (opt-in, see pdl_plan_launch)
 };
 
 constexpr size_t kPrepHeaderBytes = 16;
@@ -128,8 +128,7 @@ __global__ void __launch_bounds__(kThreads) fq_affine_kernel(const AffineArgs a)
     const int64_t remaining = a.n - t0;
     const bool full = remaining >= (int64_t)TILE;
     const T* xt = reinterpret_cast<const T*>(a.x) + t0;
-    const bool early = a.early != 0;
-    pdl_gate(!early);
+    pdl_enter(a.early);
 
     uint32_t w[UNROLL][WORDS];
     if (full) {
@@ -148,7 +147,7 @@ __global__ void __launch_bounds__(kThreads) fq_affine_kernel(const AffineArgs a)
             }
         }
     }
-    pdl_gate(early);                                   // the tile is in flight; nothing is written before this point
+    pdl_loaded(a.early);                                   // the tile is in flight; nothing is written before this point
 
     typename Op::ChanParams pu;
     Window win;
@@ -330,6 +329,7 @@ __global__ void __launch_bounds__(kThreads) fq_affine_kernel(const AffineArgs a)
             }
         }
     }
+    pdl_exit(a.early);
 }
 
 // ------------------------------------------------------------------------------------------ parameter preparation

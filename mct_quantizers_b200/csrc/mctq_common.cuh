@@ -245,33 +245,45 @@ __device__ __forceinline__ void locate(uint32_t l, const Window& w, const Args& 
 
 // ------------------------------------------------------------------------------------------ dependent launch
 // Every streaming kernel is launched with the programmatic-stream-serialization attribute and brackets its work with
-// pdl_wait() (returns once the preceding kernel in the stream has completed and its writes are visible; a no-op when the
-// launch carries no programmatic dependency) and pdl_launch_dependents(), which lets the NEXT kernel of the stream be
-// scheduled while this one is still running: its CTAs take the SM slots that free up during our tail.
+// griddepcontrol.wait (returns once the preceding kernel in the stream has completed and its writes are visible; a no-op
+// when the launch carries no programmatic dependency) and griddepcontrol.launch_dependents, which lets the NEXT kernel of
+// the stream be scheduled while this one is still running: its CTAs take the SM slots that free up during our tail.
 //
-// Two orders exist, selected per launch by the host (`early` in the kernel arguments, see pdl_plan_launch).  The early
-// order is OPT-IN (mctq_set_tuning key 3 = 2; Python: `with mct_quantizers_b200.private_stream():`): the library cannot see
-// kernels other libraries enqueue between two of its launches, and such a kernel may itself trigger its dependents before
-// it has stored its results (cuDNN / CUTLASS kernels do), so loads in front of the wait are only legal when the caller
-// guarantees that nothing else feeds these launches on the stream.  Measured on the MobileNetV2 step: +1.6 % (6656 ->
-// 6761 GB/s); an L2-prefetch-before-the-wait variant that would be legal unconditionally gained nothing (6647) and was dropped.
-//   late  : wait -> trigger -> loads -> math -> stores     the dependent CTAs sit idle in their wait during our tail
-//   early : loads -> wait -> trigger -> math -> stores     the dependent CTAs already have their tile in flight while
-//           our last wave drains: back-to-back launches (54 per MobileNetV2 step, 96 per Llama-7B weight pass) keep the
-//           memory system busy across launch boundaries.  Only legal when the kernel's INPUT cannot be an output of the
-//           kernel it overlaps with; the trigger stays behind the wait so that at most two consecutive kernels overlap.
+// Three orders exist, selected per launch by the host (`early` in the kernel arguments, see pdl_plan_launch):
+//   0 late  : wait -> trigger -> loads -> math -> stores         the default; legal whatever else runs on the stream
+//   1 early : loads -> wait -> trigger -> math -> stores         the dependent CTAs already have their tile in flight while
+//             the predecessor's last wave drains.  Needs: the input is not an output of any launch still in flight.
+//   2 free  : trigger -> loads -> math -> stores -> wait         the launch does not wait for anything until its CTAs are
+//             done: consecutive launches overlap completely, there is no drain / ramp between them.  The wait at the end
+//             keeps the stream's completion order (a kernel finishes only after its predecessor has).  Needs: inputs AND
+//             outputs are disjoint from the inputs and outputs of every launch still in flight; at most kChainMax - 1
+//             such launches in a row, then a late one.
+// Orders 1 and 2 are OPT-IN (mctq_set_tuning key 3 = 2 / 3; Python: `with mct_quantizers_b200.private_stream():`): the library
+// cannot see kernels other libraries enqueue between two of its launches -- such a kernel may itself release its dependents
+// before its stores are visible (cuDNN / CUTLASS kernels do), and the caching allocator may hand one of its input buffers
+// to a later launch of ours as output -- so they are only legal while the stream carries this library's launches alone.
+// Measured on the MobileNetV2 step (54 back-to-back launches): late 6656, early 6761 GB/s; an L2-prefetch-before-the-wait
+// variant that would be legal unconditionally gained nothing (6647) and was dropped.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_gate(bool now) { if (now) { pdl_wait(); pdl_launch_dependents(); } }
+__device__ __forceinline__ void pdl_enter(uint32_t order) {          // first statement of a streaming kernel
+    if (order == 0) pdl_wait();
+    if (order != 1) pdl_launch_dependents();
+}
+__device__ __forceinline__ void pdl_loaded(uint32_t order) {         // the tile's loads are issued; nothing has been written yet
+    if (order == 1) { pdl_wait(); pdl_launch_dependents(); }
+}
+__device__ __forceinline__ void pdl_exit(uint32_t order) {           // last statement, every thread
+    if (order == 2) pdl_wait();
+}
 
-// Host side of the early order (mctq_host.cu; only consulted when the caller opted in): the library remembers, per
-// (device, stream), the memory ranges its most recent streaming launch WRITES.  A launch may load before the wait iff none
-// of its inputs overlaps those ranges -- then the kernel it may overlap with (the previous launch of this library on the
-// stream, if it is still running) does not produce its input.  Kernels of OTHER libraries enqueued in between are invisible
-// to this bookkeeping, which is why the order is opt-in.  Launches whose outputs are not described (multi-tensor plans)
-// record "unknown", which forces the late order on their successor.
+// Host side (mctq_host.cu; consulted when the caller opted in): the library remembers, per (device, stream), the memory
+// ranges of its launches that may still be in flight -- back to the last launch that waited before touching memory -- and
+// picks the most permissive order the new launch's ranges allow.  Launches whose ranges are not described (multi-tensor
+// plans) record "unknown", which forces the late order on their successor.
 struct IoSpan { const void* p; size_t bytes; };
-int pdl_plan_launch(cudaStream_t st, const IoSpan* in, int n_in, const IoSpan* out, int n_out);   // 1 = early order allowed
+int pdl_plan_launch(cudaStream_t st, const IoSpan* in, int n_in, const IoSpan* out, int n_out);   // 0 late, 1 early, 2 free
+void pdl_forget_streams();                                           // every stream starts over with a late launch
 
 // ------------------------------------------------------------------------------------------ TMA bulk staging
 // Parameter tables that are already laid out in global memory the way a CTA wants them in shared memory (prepared LUT

@@ -21,7 +21,7 @@ struct FusedArgs {
     int64_t n;
     float scale;
     int32_t zp, qmin, qmax;
-    uint32_t early;          // loads before griddepcontrol.wait (see pdl_plan_launch)
+    uint32_t early;          // dependent-launch order: 0 late, 1 early, 2 free (see pdl_plan_launch)
 };
 
 template <typename T, int PRE>
@@ -44,8 +44,7 @@ __global__ void __launch_bounds__(kThreads) fq_affine_pre_kernel(const FusedArgs
     const bool full = remaining >= (int64_t)TILE;
     const T* xt = reinterpret_cast<const T*>(a.x) + t0;
     const T* bt = reinterpret_cast<const T*>(a.x2) + t0;
-    const bool early = a.early != 0;
-    pdl_gate(!early);
+    pdl_enter(a.early);
 
     uint32_t w[UNROLL][4], v[UNROLL][4];
 #pragma unroll
@@ -66,7 +65,7 @@ __global__ void __launch_bounds__(kThreads) fq_affine_pre_kernel(const FusedArgs
             if (TWO) memcpy(v[j], tb, 16);
         }
     }
-    pdl_gate(early);
+    pdl_loaded(a.early);
 
     const float s = a.scale;
     const float inv = __fdiv_rn(1.0f, s);
@@ -91,6 +90,7 @@ __global__ void __launch_bounds__(kThreads) fq_affine_pre_kernel(const FusedArgs
             for (int e = 0; e < V && l + e < remaining; ++e) yt[l + e] = from_f32<T>(f[e]);
         }
     }
+    pdl_exit(a.early);
 }
 
 // element-per-thread variant for misaligned views

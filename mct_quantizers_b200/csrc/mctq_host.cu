@@ -9,62 +9,94 @@ std::atomic<int64_t> g_launches{0};
 int g_unroll = 0;           // 0 = automatic (per-tensor tiles: 2 vectors per thread, per-channel tiles: 4)
 int g_force_rint = 0;
 int g_force_ieee_div = 0;
-int g_pdl = 1;              // 0 off, 1 programmatic dependent launch (wait first), 2 (opt-in) + loads before the wait when the input is not the previous launch's output
+int g_pdl = 1;              // 0 off, 1 programmatic dependent launch (wait first), opt-in: 2 + loads before the wait, 3 + no wait at all for launches independent of everything still in flight
 int g_lut_shfl = 1;
 int g_wide = 1;             // 8-element vectors / 256-bit stores where a kernel has them (key 5)
 int g_lut_xy = 1;           // key 7
 int g_multi_span = 4;       // tiles per CTA in the multi-tensor LUT launch: 1 or 4 (key 6; read when a plan is compiled)
 
-// ---- early-order bookkeeping (see mctq_common.cuh): what did the last streaming launch on (device, stream) write?
+// ---- dependent-launch bookkeeping (see mctq_common.cuh): per (device, stream), the memory ranges of the library's launches
+// since -- and including -- the last one that waited for its predecessor BEFORE touching memory (a "late" launch: when its
+// first CTA passes the wait, everything enqueued before it has completed).  Every launch after it may still be running
+// together with it, so a new launch is checked against the whole chain.
 namespace {
-struct LastLaunch {
+struct Span { uintptr_t lo, hi; };
+struct ChainLaunch {
+    int n_in, n_out;        // -1 / -1: ranges unknown (multi-tensor plans): nothing may overlap with it
+    Span in[2], out[2];
+};
+constexpr int kChainMax = 3;             // a late launch + at most two launches that overlap with it, then a late one again
+struct StreamChain {
     cudaStream_t st;
     int device;
-    int n_out;              // -1: outputs unknown
     uint64_t stamp;
-    uintptr_t lo[2], hi[2];
+    int n;
+    ChainLaunch l[kChainMax];
 };
 constexpr int kLastSlots = 16;
-LastLaunch g_last[kLastSlots];
-uint64_t g_last_stamp = 0;
-std::mutex g_last_mu;
+StreamChain g_chain[kLastSlots];
+uint64_t g_chain_stamp = 0;
+std::mutex g_chain_mu;
+
+inline bool overlaps(const Span& a, const Span& b) { return a.lo < b.hi && b.lo < a.hi; }
 }  // namespace
+
+void pdl_forget_streams() {
+    std::lock_guard<std::mutex> lock(g_chain_mu);
+    for (auto& c : g_chain) c.stamp = 0;
+}
 
 int pdl_plan_launch(cudaStream_t st, const IoSpan* in, int n_in, const IoSpan* out, int n_out) {
     if (g_pdl == 0) return 0;
     int device = 0;
     if (cudaGetDevice(&device) != cudaSuccess) { cudaGetLastError(); return 0; }
-    std::lock_guard<std::mutex> lock(g_last_mu);
-    LastLaunch* slot = nullptr;
-    LastLaunch* victim = &g_last[0];
-    for (int i = 0; i < kLastSlots; ++i) {
-        LastLaunch& l = g_last[i];
-        if (l.stamp && l.st == st && l.device == device) { slot = &l; break; }
-        if (l.stamp < victim->stamp) victim = &l;
+    ChainLaunch me;
+    me.n_in = me.n_out = -1;
+    if (in && out) {
+        me.n_in = me.n_out = 0;
+        for (int i = 0; i < n_in && i < 2; ++i)
+            if (in[i].p && in[i].bytes) me.in[me.n_in++] = {reinterpret_cast<uintptr_t>(in[i].p), reinterpret_cast<uintptr_t>(in[i].p) + in[i].bytes};
+        for (int j = 0; j < n_out && j < 2; ++j)
+            if (out[j].p && out[j].bytes) me.out[me.n_out++] = {reinterpret_cast<uintptr_t>(out[j].p), reinterpret_cast<uintptr_t>(out[j].p) + out[j].bytes};
     }
-    int early = g_pdl >= 2 && in != nullptr;
-    if (slot && early) {
-        if (slot->n_out < 0) early = 0;
-        for (int i = 0; early && i < n_in; ++i) {
-            const uintptr_t lo = reinterpret_cast<uintptr_t>(in[i].p), hi = lo + in[i].bytes;
-            for (int j = 0; j < slot->n_out; ++j)
-                if (in[i].p && lo < slot->hi[j] && slot->lo[j] < hi) early = 0;
+    std::lock_guard<std::mutex> lock(g_chain_mu);
+    StreamChain* slot = nullptr;
+    StreamChain* victim = &g_chain[0];
+    for (int i = 0; i < kLastSlots; ++i) {
+        StreamChain& c = g_chain[i];
+        if (c.stamp && c.st == st && c.device == device) { slot = &c; break; }
+        if (c.stamp < victim->stamp) victim = &c;
+    }
+    // 0 late (wait, then everything), 1 early (loads before the wait), 2 free (no wait until the CTA's last instruction)
+    int order = 0;
+    if (g_pdl >= 2 && slot && me.n_in >= 0) {
+        bool raw = false, other = false, unknown = false;       // input produced by the chain / output collides with the chain
+        for (int k = 0; k < slot->n; ++k) {
+            const ChainLaunch& c = slot->l[k];
+            if (c.n_in < 0) { unknown = true; break; }
+            for (int i = 0; i < me.n_in; ++i)
+                for (int j = 0; j < c.n_out; ++j) raw |= overlaps(me.in[i], c.out[j]);
+            for (int i = 0; i < me.n_out; ++i) {
+                for (int j = 0; j < c.n_out; ++j) other |= overlaps(me.out[i], c.out[j]);
+                for (int j = 0; j < c.n_in; ++j) other |= overlaps(me.out[i], c.in[j]);
+            }
         }
+        if (!unknown && !raw) order = (g_pdl >= 3 && !other && slot->n < kChainMax) ? 2 : 1;
     }
     // a stream this table has never seen (or whose entry was evicted): the predecessor may be one of our launches that
     // is no longer remembered -> late order
-    if (!slot) { early = 0; slot = victim; }
+    if (!slot) { slot = victim; slot->n = 0; }
     slot->st = st;
     slot->device = device;
-    slot->stamp = ++g_last_stamp;
-    slot->n_out = out ? 0 : -1;
-    for (int j = 0; out && j < n_out && j < 2; ++j) {
-        if (!out[j].p) continue;
-        slot->lo[slot->n_out] = reinterpret_cast<uintptr_t>(out[j].p);
-        slot->hi[slot->n_out] = slot->lo[slot->n_out] + out[j].bytes;
-        ++slot->n_out;
+    slot->stamp = ++g_chain_stamp;
+    if (order == 2) {
+        slot->l[slot->n++] = me;                     // runs alongside the whole chain
+    } else {
+        // a launch that waits (before its stores at the latest) ends the overlap: whoever follows can only meet this launch
+        slot->l[0] = me;
+        slot->n = 1;
     }
-    return early;
+    return order;
 }
 }  // namespace mctq
 
@@ -86,7 +118,7 @@ int mctq_set_tuning(int key, int value) {
         case 0: prev = g_unroll; if (value != 0 && value != 2 && value != 4 && value != 8) return MCTQ_E_BADARG; g_unroll = value; return prev;
         case 1: prev = g_force_rint; g_force_rint = value ? 1 : 0; return prev;
         case 2: prev = g_force_ieee_div; g_force_ieee_div = value ? 1 : 0; return prev;
-        case 3: prev = g_pdl; if (value < 0 || value > 2) return MCTQ_E_BADARG; g_pdl = value; return prev;
+        case 3: prev = g_pdl; if (value < 0 || value > 3) return MCTQ_E_BADARG; g_pdl = value; pdl_forget_streams(); return prev;
         case 4: prev = g_lut_shfl; g_lut_shfl = value ? 1 : 0; return prev;
         case 5: prev = g_wide; if (value < 0 || value > 2) return MCTQ_E_BADARG; g_wide = value; return prev;
         case 7: prev = g_lut_xy; g_lut_xy = value ? 1 : 0; return prev;

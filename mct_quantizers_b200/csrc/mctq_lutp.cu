@@ -180,7 +180,7 @@ struct LutPArgs {
     int64_t C, inner, elem_offset;
     FastDiv div_inner, div_W;
     uint32_t W, bigrow;
-    uint32_t early;          // loads before griddepcontrol.wait (opt-in order, see pdl_plan_launch)
+    uint32_t early;          // dependent-launch order: 0 late, 1 early, 2 free (opt-in, see pdl_plan_launch)
 };
 
 __device__ __forceinline__ float fma_sat(float a, float b, float c) {
@@ -218,8 +218,7 @@ __device__ __forceinline__ void lutp_tile(const LutPArgs& a, const int64_t tile_
     const int64_t remaining = a.n - t0;
     const bool full = remaining >= (int64_t)TILE;
     const T* xt = reinterpret_cast<const T*>(a.x) + t0;
-    const bool early = a.early != 0;
-    pdl_gate(!early);
+    pdl_enter(a.early);
     uint32_t tab_bytes = 0;                                           // bytes of FRONT in use: fetched while the tile loads are issued
     if (tid == 0) tab_bytes = (uint32_t)__ldg(&reinterpret_cast<const LutPrepHeader*>(a.blob)->front_bytes);
 
@@ -241,7 +240,7 @@ __device__ __forceinline__ void lutp_tile(const LutPArgs& a, const int64_t tile_
         }
     }
 
-    pdl_gate(early);                                                  // the tile is in flight; nothing is written before this point
+    pdl_loaded(a.early);                                                  // the tile is in flight; nothing is written before this point
 
     // Stage the decision tables with the bulk-copy engine (1-D TMA): the blob already holds them in the layout the
     // CTA wants -- [cells | orig] contiguous and channel records back to back -- so one elected thread arms the
@@ -410,6 +409,7 @@ __device__ __forceinline__ void lutp_tile(const LutPArgs& a, const int64_t tile_
     };
     if (CODE != 0 && __ldg(&reinterpret_cast<const LutPrepHeader*>(a.blob)->orig_identity) != 0) run(std::true_type{});
     else run(std::false_type{});
+    pdl_exit(a.early);
 }
 
 // ---- xy variant: per-tensor thresholds or rows at least one tile long (a tile touches at most two channels), centroid
@@ -485,8 +485,7 @@ __device__ __forceinline__ void lutx_tile(const LutPArgs& a, const int64_t tile_
     const int64_t remaining = a.n - t0;
     const bool full = remaining >= (int64_t)TILE;
     const T* xt = reinterpret_cast<const T*>(a.x) + t0;
-    const bool early = a.early != 0;
-    pdl_gate(!early);
+    pdl_enter(a.early);
     uint32_t tab_bytes = 0;
     if (tid == 0) tab_bytes = (uint32_t)__ldg(&reinterpret_cast<const LutPrepHeader*>(a.blob)->front_bytes);
 
@@ -508,7 +507,7 @@ __device__ __forceinline__ void lutx_tile(const LutPArgs& a, const int64_t tile_
         }
     }
 
-    pdl_gate(early);                                                  // the tile is in flight; nothing is written before this point
+    pdl_loaded(a.early);                                                  // the tile is in flight; nothing is written before this point
 
     const uint32_t Wn = CHMODE == CH_PT ? 1u : a.W;                   // channel slots (rows a tile can touch; <= kXyMaxW)
     float* sm_rec = sm_dyn;
@@ -617,6 +616,7 @@ __device__ __forceinline__ void lutx_tile(const LutPArgs& a, const int64_t tile_
             }
         }
     }
+    pdl_exit(a.early);
 }
 
 template <typename T, int CHMODE, int CODE, int UNROLL, int V>

@@ -638,15 +638,20 @@ def _lut_scalar_cuda(x, table, K, divisor, threshold, round_to_input_dtype):
 
 class private_stream:
     """Context manager for back-to-back calls on tensors that ALREADY EXIST (per-layer weight quantization of a model,
-    sweeps over recorded activations): inside the block a launch whose input is not an output of this package's previous
-    launch on the stream issues its loads BEFORE waiting for that launch (programmatic dependent launch, early order), so
-    the next kernel's reads overlap the previous kernel's drain (+1.6 % on 54 back-to-back launches, +3-6 % on 64 MB
-    tensors).  The caller guarantees that no OTHER library's kernel enqueued inside the block produces an input of a call
-    inside the block (a cuDNN / cuBLAS kernel may release its dependents before its stores are visible).  Process-wide
-    setting; restores the previous one on exit."""
+    sweeps over recorded activations): inside the block consecutive launches of this package on a stream may OVERLAP.  A
+    launch whose buffers are disjoint from those of every launch still in flight does not wait for its predecessor at all
+    (at most two such launches in a row), one whose input is merely not produced by a launch in flight issues its loads
+    before it waits -- the drain of one kernel and the ramp of the next disappear (programmatic dependent launch, orders
+    "free" and "early" in csrc/mctq_common.cuh; every dependency between this package's own launches is detected from
+    their address ranges and honoured).
+
+    The caller guarantees that, inside the block, the streams used carry NO OTHER work than this package's calls: the
+    library cannot see foreign kernels (a cuDNN kernel may release its dependents before its stores are visible; the
+    caching allocator may recycle a foreign kernel's input buffer as one of our outputs).  Entering and leaving the block
+    make the next launch on every stream wait for everything before it.  Process-wide setting."""
 
     def __enter__(self):
-        self._prev = _native.load().mctq_set_tuning(3, 2)
+        self._prev = _native.load().mctq_set_tuning(3, 3)
         return self
 
     def __exit__(self, *exc):
@@ -781,9 +786,24 @@ def _lut_scalar_cpu(x, table, K, divisor, threshold, round_to_input_dtype):
     return _lut_host(x, table, K, None, 1, 1, 0.0, 1, divisor, threshold, round_to_input_dtype)
 
 
-def _no_host_path(name):
-    def impl(*args, **kwargs):
-        raise MctqError(f"mctq::{name} needs CUDA tensors (integer-code emission has no host-buffer entry point)")
+def _via_device(cuda_impl, keep=()):
+    """Host-tensor implementation of the operators that have no chunked host pipeline of their own (integer codes, LUT
+    indices, dequantization, the producer-fused holder): every tensor argument is copied to the current CUDA device, the
+    device operator runs there and the results come back as host tensors.  Codes are the cheap direction of this trip:
+    one byte (or a nibble) per element returns instead of four.  `keep`: positions of tensor arguments that stay on the
+    host (the LUT search table is host data by contract)."""
+    def impl(*args):
+        dev = torch.device("cuda", _require_cuda_for_host_path())
+
+        def up(a):
+            if isinstance(a, torch.Tensor) and not a.is_cuda:
+                return a.to(dev, non_blocking=a.is_pinned())
+            return a
+
+        out = cuda_impl(*[a if k in keep else up(a) for k, a in enumerate(args)])
+        if isinstance(out, (tuple, list)):
+            return type(out)(o.cpu() if isinstance(o, torch.Tensor) else o for o in out)
+        return out.cpu() if isinstance(out, torch.Tensor) else out
     return impl
 
 
@@ -797,15 +817,15 @@ _LIB.impl("dequantize_affine", _dequantize_affine_cuda, "CUDA")
 _LIB.impl("lut_indices", _lut_indices_cuda, "CUDA")
 
 _LIB.impl("fq_affine_scalar_pre", _affine_scalar_pre_cuda, "CUDA")
-_LIB.impl("fq_affine_scalar_pre", _no_host_path("fq_affine_scalar_pre"), "CPU")
+_LIB.impl("fq_affine_scalar_pre", _via_device(_affine_scalar_pre_cuda), "CPU")
 _LIB.impl("fq_affine_scalar", _affine_scalar_cpu, "CPU")
 _LIB.impl("fq_affine_tensor", _affine_tensor_cpu, "CPU")
 _LIB.impl("fq_affine_channel", _affine_channel_cpu, "CPU")
 _LIB.impl("fq_lut_tensor", _lut_tensor_cpu, "CPU")
 _LIB.impl("fq_lut_scalar", _lut_scalar_cpu, "CPU")
-_LIB.impl("quantize_affine_channel", _no_host_path("quantize_affine_channel"), "CPU")
-_LIB.impl("dequantize_affine", _no_host_path("dequantize_affine"), "CPU")
-_LIB.impl("lut_indices", _no_host_path("lut_indices"), "CPU")
+_LIB.impl("quantize_affine_channel", _via_device(_quantize_affine_channel_cuda), "CPU")
+_LIB.impl("dequantize_affine", _via_device(_dequantize_affine_cuda), "CPU")
+_LIB.impl("lut_indices", _via_device(_lut_indices_cuda, keep=(1,)), "CPU")
 
 
 # --------------------------------------------------------------------------------------------- fake / meta impls

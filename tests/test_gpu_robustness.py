@@ -239,7 +239,7 @@ def test_private_stream_early_order_keeps_dependent_chains_correct(Q):
     want = chain()
     torch.cuda.synchronize()
     with mctq.private_stream():
-        assert _native.load().mctq_set_tuning(3, 2) == 2
+        assert _native.load().mctq_set_tuning(3, 3) == 3
         got = chain()
         s = torch.cuda.Stream()
         with torch.cuda.stream(s):                     # a stream the library has not seen: first launch falls back to the late order
@@ -250,3 +250,73 @@ def test_private_stream_early_order_keeps_dependent_chains_correct(Q):
     torch.cuda.synchronize()
     for a, b, c in zip(want, got, got2):
         assert torch.equal(a, b) and torch.equal(a, c)
+
+
+def test_code_emission_and_dequant_accept_host_tensors(Q):
+    """quantize_affine_channel / dequantize_affine / lut_indices / the producer-fused op on HOST tensors: computed on the GPU
+    (copied up, codes copied back), same bits as the device call and the oracle."""
+    from mct_quantizers_b200.pytorch.quantizer_utils import lut_search_table
+    rng = np.random.default_rng(9)
+    w = torch.from_numpy(rng.standard_normal((12, 40)).astype(np.float32))
+    thr = w.abs().amax(1)
+    scale = (thr / 128).float()
+    zp = torch.zeros(12, dtype=torch.int32)
+    codes_h, y_h = torch.ops.mctq.quantize_affine_channel(w, scale, zp, 0, -128, 127, 1, True)
+    codes_d, y_d = torch.ops.mctq.quantize_affine_channel(w.to(DEV), scale.to(DEV), zp.to(DEV), 0, -128, 127, 1, True)
+    assert not codes_h.is_cuda and not y_h.is_cuda
+    assert torch.equal(codes_h, codes_d.cpu()) and torch.equal(y_h, y_d.cpu())
+    want, want_codes = oracle.fq_affine(w.numpy(), oracle.F32, scale.numpy(), zp.numpy(), 12, 40, -128, 127, want_codes=True)
+    assert G.bits_equal(y_h.numpy(), np.asarray(want).reshape(y_h.shape))
+    assert np.array_equal(codes_h.numpy().astype(np.int32).reshape(-1), np.asarray(want_codes).reshape(-1))
+    back = torch.ops.mctq.dequantize_affine(codes_h, 1, True, list(w.shape), scale, zp, 0)
+    assert not back.is_cuda and torch.equal(back, y_h)
+    lut = [float(v) for v in sorted(rng.choice(np.arange(-128, 128), size=16, replace=False))]
+    table = lut_search_table(np.asarray(lut, np.float32), 8, True)
+    i_h = torch.ops.mctq.lut_indices(w, table, 16, thr.float(), True, 0, 1e-8, 2)
+    i_d = torch.ops.mctq.lut_indices(w.to(DEV), table, 16, thr.float().to(DEV), True, 0, 1e-8, 2)
+    assert not i_h.is_cuda and torch.equal(i_h, i_d.cpu())
+    f_h = torch.ops.mctq.fq_affine_scalar_pre(w, None, 1, 0.02, 0, 0, 255)
+    assert not f_h.is_cuda and torch.equal(f_h, torch.ops.mctq.fq_affine_scalar_pre(w.to(DEV), None, 1, 0.02, 0, 0, 255).cpu())
+
+
+def test_private_stream_orders_respect_every_hazard_between_own_launches():
+    """Opt-in overlap (orders "early" / "free"): sequences with read-after-write, write-after-read and write-after-write
+    hazards between consecutive launches of the library give the bits of the default order.  Large tensors, so that
+    consecutive kernels really could overlap."""
+    import ctypes
+    from mct_quantizers_b200 import _native
+    lib = _native.load()
+    n = 48 << 20
+    g = torch.Generator(device=DEV).manual_seed(11)
+    src = [torch.empty(n, device=DEV).uniform_(-4, 4, generator=g) for _ in range(3)]
+    st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)  # noqa: E731
+
+    def fq(a, b, scale, m=n):
+        assert lib.mctq_fq_affine_scalar(ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(b.data_ptr()), None, m, 0, scale, 3, 0, 255, 0, st()) == 0
+
+    def sequence():
+        x, z, u = (t.clone() for t in src)
+        y, w, v = torch.empty(n, device=DEV), torch.empty(n, device=DEV), torch.empty(n, device=DEV)
+        torch.cuda.synchronize()
+        fq(x, y, 0.031)              # A
+        fq(z, x, 0.017)              # B writes A's input            (write-after-read)
+        fq(x, w, 0.023)              # C reads B's output            (read-after-write)
+        fq(u, w[: n // 2], 0.011, n // 2)   # D overwrites half of C's output (write-after-write)
+        fq(u, v, 0.05)               # E, F, G: independent of everything in flight -> may run without waiting
+        fq(z, y, 0.04)               # (y was A's output: A has long finished being relevant, but the range check must hold)
+        fq(v, u, 0.02)               # reads E's output, writes E's input
+        for k in range(6):           # a run of independent launches: every third one must wait again
+            fq(src[k % 3], [y, w, v][k % 3], 0.01 * (k + 1))
+        torch.cuda.synchronize()
+        return [t.clone() for t in (x, y, w, v, u)]
+
+    want = sequence()
+    for mode in (2, 3):
+        prev = lib.mctq_set_tuning(3, mode)
+        try:
+            for _ in range(3):
+                got = sequence()
+                for a, b in zip(want, got):
+                    assert torch.equal(a, b), mode
+        finally:
+            lib.mctq_set_tuning(3, prev)
