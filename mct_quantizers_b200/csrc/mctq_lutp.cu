@@ -544,78 +544,100 @@ __device__ __forceinline__ void lutx_tile(const LutPArgs& a, const int64_t tile_
     const float based = __uint_as_float(front_s + a.rel_cells);       // &cells[0] * 2^-149
     const uint32_t orig_s = front_s + a.rel_orig;
     float* yt = a.y + t0;
-    bool ident = true;
-    if (CODE != 0) ident = __ldg(&reinterpret_cast<const LutPrepHeader*>(a.blob)->orig_identity) != 0;
+    // Index emission packs as it goes: element e adds pos << (4e) (nibbles) or pos << (8 (e & 3)) (bytes) to a 32-bit
+    // accumulator -- one shift-add per element, no per-element code registers (a first version kept V codes and masked /
+    // shifted / or-ed them at the end: 21 instructions per element and 58-64 registers for bf16).  When the centroid list
+    // is sorted and free of duplicates the sorted position IS the LUT index (flag in the blob header).
+    auto run = [&](auto ident_tag) {
+        constexpr bool IDENT = decltype(ident_tag)::value;
+        constexpr int CW = CODE == MCTQ_CODES_INT8 ? V / 4 : 1;
 #pragma unroll
-    for (int j = 0; j < UNROLL; ++j) {
-        const uint32_t l = (uint32_t)(j * kThreads + tid) * V;
-        float f[V];
-        int code[V];
-        Pack<T, V>::unpack(w[j], f);
-        uint32_t slot = 0, rem = 0;
-        if (CHMODE != CH_PT) locate(l, win, a, slot, rem);
-        const uint32_t rec = rec_s + slot * REC;
-        const float sp = lds_f32(rec + 2u * kXyP * 4u);
-        // staged so that the V independent look-up chains of a vector are in flight together
-        uint32_t ca[V], bb[V];
+        for (int j = 0; j < UNROLL; ++j) {
+            const uint32_t l = (uint32_t)(j * kThreads + tid) * V;
+            float f[V];
+            uint32_t cw[CW];
 #pragma unroll
-        for (int e = 0; e < V; ++e) {
-            const float u = fma_sat(f[e], sp, c0f);                           // saturates to [0, 1]; NaN -> 0
-            ca[e] = __float_as_uint(__fmaf_rn(u, NCd, based));                // address of this element's cell
-        }
+            for (int i = 0; i < CW; ++i) cw[i] = 0;
+            Pack<T, V>::unpack(w[j], f);
+            uint32_t slot = 0, rem = 0;
+            if (CHMODE != CH_PT) locate(l, win, a, slot, rem);
+            const uint32_t rec = rec_s + slot * REC;
+            const float sp = lds_f32(rec + 2u * kXyP * 4u);
+            // staged so that the V independent look-up chains of a vector are in flight together
+            uint32_t ca[V], bb[V];
 #pragma unroll
-        for (int e = 0; e < V; ++e) bb[e] = lds_u8(ca[e]);                    // index of the candidate threshold
-#pragma unroll
-        for (int e = 0; e < V; ++e) {
-            const uint32_t ea = rec + (bb[e] << 2);
-            if (CODE != 0) {
-                bool above;
-                f[e] = xy_select(f[e], ea, above);
-                const uint32_t pos = bb[e] + (above ? 1u : 0u);
-                code[e] = ident ? (int)pos : (int)lds_u8(orig_s + pos);
-            } else {
-                f[e] = xy_select(f[e], ea);
-            }
-        }
-        if (NanProbe<T>::template any<WORDS_IN>(w[j])) {
-            // rare: torch.argmin over all-NaN distances returns index 0 of the ORIGINAL centroid list
-            const uint32_t pos0 = (uint32_t)__ldg(&reinterpret_cast<const LutPrepHeader*>(a.blob)->pos0);
-            float g[V];
-            Pack<T, V>::unpack(w[j], g);
             for (int e = 0; e < V; ++e) {
-                if (g[e] != g[e]) {
-                    f[e] = lds_f32(rec + (kXyP + pos0) * 4u);
-                    if (CODE != 0) code[e] = (int)lds_u8(orig_s + pos0);
+                const float u = fma_sat(f[e], sp, c0f);                           // saturates to [0, 1]; NaN -> 0
+                ca[e] = __float_as_uint(__fmaf_rn(u, NCd, based));                // address of this element's cell
+            }
+#pragma unroll
+            for (int e = 0; e < V; ++e) bb[e] = lds_u8(ca[e]);                    // index of the candidate threshold
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                const uint32_t ea = rec + (bb[e] << 2);
+                if (CODE != 0) {
+                    bool above;
+                    f[e] = xy_select(f[e], ea, above);
+                    uint32_t pos = bb[e] + (above ? 1u : 0u);
+                    if (!IDENT) pos = lds_u8(orig_s + pos);
+                    if (CODE == MCTQ_CODES_INT4) cw[0] += pos << (4 * e);
+                    else cw[e >> 2] += pos << (8 * (e & 3));
+                } else {
+                    f[e] = xy_select(f[e], ea);
                 }
             }
-        }
-        if (full || (int64_t)l + V <= remaining) {
-            if (a.y) {
-                uint32_t o[V];
-                Pack<float, V>::pack(f, o);
-                if (V == 8) st_stream256(yt + l, o);
-                else st_words<4>(yt + l, o);
-            }
-            if (CODE != 0) st_codes<V, CODE>(a.idx, t0 + l, code);
-        } else if ((int64_t)l < remaining) {
-            const int cnt = (int)(remaining - l);
-            for (int e = 0; e < V; ++e) {
-                if (e < cnt) {
-                    if (a.y) yt[l + e] = f[e];
-                    if (CODE == MCTQ_CODES_INT8) reinterpret_cast<uint8_t*>(a.idx)[t0 + l + e] = (uint8_t)code[e];
+            if (NanProbe<T>::template any<WORDS_IN>(w[j])) {
+                // rare: torch.argmin over all-NaN distances returns index 0 of the ORIGINAL centroid list
+                const uint32_t pos0 = (uint32_t)__ldg(&reinterpret_cast<const LutPrepHeader*>(a.blob)->pos0);
+                float g[V];
+                Pack<T, V>::unpack(w[j], g);
+                for (int e = 0; e < V; ++e) {
+                    if (g[e] != g[e]) {
+                        f[e] = lds_f32(rec + (kXyP + pos0) * 4u);
+                        if (CODE == MCTQ_CODES_INT4) cw[0] = (cw[0] & ~(0xfu << (4 * e))) | (lds_u8(orig_s + pos0) << (4 * e));
+                        if (CODE == MCTQ_CODES_INT8) cw[e >> 2] = (cw[e >> 2] & ~(0xffu << (8 * (e & 3)))) | (lds_u8(orig_s + pos0) << (8 * (e & 3)));
+                    }
                 }
             }
-            if (CODE == MCTQ_CODES_INT4) {
-                uint8_t* cp = reinterpret_cast<uint8_t*>(a.idx) + ((t0 + l) >> 1);
-                for (int e = 0; e < V; e += 2) {
+            if (full || (int64_t)l + V <= remaining) {
+                if (a.y) {
+                    uint32_t o[V];
+                    Pack<float, V>::pack(f, o);
+                    if (V == 8) st_stream256(yt + l, o);
+                    else st_words<4>(yt + l, o);
+                }
+                if (CODE == MCTQ_CODES_INT8) {
+                    uint8_t* cp = reinterpret_cast<uint8_t*>(a.idx) + t0 + l;
+                    if (V == 4) st_stream(reinterpret_cast<uint32_t*>(cp), cw[0]);
+                    else st_stream(reinterpret_cast<uint2*>(cp), make_uint2(cw[0], cw[CW - 1]));
+                } else if (CODE == MCTQ_CODES_INT4) {
+                    uint8_t* cp = reinterpret_cast<uint8_t*>(a.idx) + ((t0 + l) >> 1);
+                    if (V == 4) st_stream(reinterpret_cast<uint16_t*>(cp), (uint16_t)cw[0]);
+                    else st_stream(reinterpret_cast<uint32_t*>(cp), cw[0]);
+                }
+            } else if ((int64_t)l < remaining) {
+                const int cnt = (int)(remaining - l);
+                for (int e = 0; e < V; ++e) {
                     if (e < cnt) {
-                        int hi = (e + 1 < cnt) ? code[e + 1] : 0;
-                        cp[e >> 1] = (uint8_t)((code[e] & 0xf) | ((hi & 0xf) << 4));
+                        if (a.y) yt[l + e] = f[e];
+                        if (CODE == MCTQ_CODES_INT8) reinterpret_cast<uint8_t*>(a.idx)[t0 + l + e] = (uint8_t)(cw[e >> 2] >> (8 * (e & 3)));
+                    }
+                }
+                if (CODE == MCTQ_CODES_INT4) {
+                    uint8_t* cp = reinterpret_cast<uint8_t*>(a.idx) + ((t0 + l) >> 1);
+                    for (int e = 0; e < V; e += 2) {
+                        if (e < cnt) {
+                            const uint32_t lo4 = (cw[0] >> (4 * e)) & 0xfu;
+                            const uint32_t hi4 = (e + 1 < cnt) ? (cw[0] >> (4 * e + 4)) & 0xfu : 0u;
+                            cp[e >> 1] = (uint8_t)(lo4 | (hi4 << 4));
+                        }
                     }
                 }
             }
         }
-    }
+    };
+    if (CODE != 0 && __ldg(&reinterpret_cast<const LutPrepHeader*>(a.blob)->orig_identity) == 0) run(std::false_type{});
+    else run(std::true_type{});
     pdl_exit(a.early);
 }
 
@@ -736,6 +758,8 @@ bool lutx_eligible(const LutPArgs& a, int chmode, int v) {
 }
 size_t lutx_smem(const LutPArgs& a, int chmode) { return (size_t)(chmode == CH_PT ? 1u : a.W) * kXyRecFloats * 4 + a.front_cap; }
 
+// (half-size tiles, UNROLL = 2, were measured on the B200 and are slower: f32 6717 -> 6320 GB/s, bf16 6836 -> 6599, Llama-7B
+// per-layer bf16 6110 -> 5839 -- the per-tile staging and barrier outweigh the finer tail)
 template <typename T, int CHMODE, int CODE, int V>
 int launch_lutx_tiles(const LutPArgs& a_in, cudaStream_t st) {
     constexpr int UNROLL = 4;
