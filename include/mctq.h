@@ -289,7 +289,10 @@ int64_t mctq_launch_count(void);
  * key 4 = warp-shuffle search in the generic LUT kernel for tables of <= 32 entries (default 1),
  * key 5 = wide vectors (8 elements per vector, 256-bit stores) in the kernels that have them (default 1),
  * key 6 = (retired: the multi-tensor LUT launches run one tile per CTA; the key is accepted and ignored),
- * key 7 = xy-record variant of the prepared LUT kernel for per-tensor / long-row launches (default 1);
+ * key 7 = xy-record variant of the prepared LUT kernel for per-tensor / long-row launches (default 1),
+ * key 8 = kernels stage their prepared parameter tables BEFORE the dependent-launch wait whenever the blob was not written by
+ *   a prepare call still in flight on the stream (default 1; the blobs are private to the library, so this is legal whatever
+ *   else runs on the stream);
  * returns previous value or <0 */
 int mctq_set_tuning(int key, int value);
 /* device self-test of the 5-op correctly-rounded division used by the LUT kernels against __fdiv_rn

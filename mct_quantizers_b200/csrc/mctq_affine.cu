@@ -32,6 +32,7 @@ struct AffineArgs {
     const int32_t* prep_flags;   // [0] != 0: some zero point is non-zero
     int64_t C4;
     uint32_t early;              // dependent-launch order: 0 late, 1 early, 2 free (opt-in, see pdl_plan_launch)
+    uint32_t tab_early;          // PREP: the parameter blob may be staged before the dependent-launch wait (nobody is writing it)
 };
 
 constexpr size_t kPrepHeaderBytes = 16;
@@ -128,35 +129,13 @@ __global__ void __launch_bounds__(kThreads) fq_affine_kernel(const AffineArgs a)
     const int64_t remaining = a.n - t0;
     const bool full = remaining >= (int64_t)TILE;
     const T* xt = reinterpret_cast<const T*>(a.x) + t0;
-    pdl_enter(a.early);
-
-    uint32_t w[UNROLL][WORDS];
-    if (full) {
-#pragma unroll
-        for (int j = 0; j < UNROLL; ++j) ld_words<WORDS>(xt + (size_t)(j * kThreads + tid) * V, w[j]);
-    } else {
-#pragma unroll
-        for (int j = 0; j < UNROLL; ++j) {
-            int64_t l = (int64_t)(j * kThreads + tid) * V;
-            if (l + V <= remaining) ld_words<WORDS>(xt + l, w[j]);
-            else {
-                T tmp[V];
-#pragma unroll
-                for (int e = 0; e < V; ++e) tmp[e] = (l + e < remaining) ? xt[l + e] : from_f32<T>(0.0f);
-                memcpy(w[j], tmp, VB);
-            }
-        }
-    }
-    pdl_loaded(a.early);                                   // the tile is in flight; nothing is written before this point
-
-    typename Op::ChanParams pu;
-    Window win;
-    uint32_t base_mod = 0;
     bool has_zp = true;
-    if (CHMODE == CH_PT) {
-        pu = Op::uniform(a);
-    } else if (PREP) {
-        if (tid == 0) {
+    // PREP: one elected thread arms the mbarrier and hands the tile's channel window to the bulk-copy engine.  When the
+    // host knows that the blob is not being written (tab_early) this happens BEFORE the dependent-launch wait, so a CTA
+    // scheduled into the predecessor's tail has its parameters in shared memory when the wait returns.
+    if constexpr (PREP && CHMODE != CH_PT) {
+        auto stage = [&]() {
+            if (tid != 0) return;
             mbar_init(&sm_bar, 1);
             if (CHMODE == CH_LAST) {
                 // period / C back-to-back copies of each parameter array: entry i = channel i % C
@@ -180,9 +159,45 @@ __global__ void __launch_bounds__(kThreads) fq_affine_kernel(const AffineArgs a)
                 bulk_g2s(sm_par, a.prep_rec + c0, n1 * 16u, &sm_bar);
                 if (n1 < a.W) bulk_g2s(sm_par + 4u * n1, a.prep_rec, (a.W - n1) * 16u, &sm_bar);
             }
+        };
+        // staging always precedes the tile loads; what moves is the wait (the host only picks an order other than "late"
+        // together with tab_early)
+        if (!a.tab_early) pdl_enter(0);
+        stage();
+        if (a.tab_early) pdl_enter(a.early);
+    } else {
+        pdl_enter(a.early);
+    }
+
+    uint32_t w[UNROLL][WORDS];
+    if (full) {
+#pragma unroll
+        for (int j = 0; j < UNROLL; ++j) ld_words<WORDS>(xt + (size_t)(j * kThreads + tid) * V, w[j]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < UNROLL; ++j) {
+            int64_t l = (int64_t)(j * kThreads + tid) * V;
+            if (l + V <= remaining) ld_words<WORDS>(xt + l, w[j]);
+            else {
+                T tmp[V];
+#pragma unroll
+                for (int e = 0; e < V; ++e) tmp[e] = (l + e < remaining) ? xt[l + e] : from_f32<T>(0.0f);
+                memcpy(w[j], tmp, VB);
+            }
         }
-        if (CHMODE == CH_LAST) base_mod = (uint32_t)((uint64_t)(a.elem_offset + t0) % a.period);
+    }
+    pdl_loaded(a.early);                                   // the tile is in flight; nothing is written before this point
+
+    typename Op::ChanParams pu;
+    Window win;
+    uint32_t base_mod = 0;
+    if (CHMODE == CH_PT) {
+        pu = Op::uniform(a);
+    } else if (PREP) {
+        // (read after the tile loads are issued: every thread needs it, and a wait in front of the loads would serialise
+        // an L2 round trip with them)
         if (CHMODE == CH_LAST || CHMODE == CH_ELEM) has_zp = __ldg(a.prep_flags) != 0;
+        if (CHMODE == CH_LAST) base_mod = (uint32_t)((uint64_t)(a.elem_offset + t0) % a.period);
         __syncthreads();                                               // barrier init + window visible to everyone
         if (CHMODE != CH_LAST) win = sm_win;
         mbar_wait(&sm_bar, 0);
@@ -752,7 +767,13 @@ int launch_affine_tiles(const AffineArgs& a_in, cudaStream_t st) {
     if (tiles > 0x7fffffffLL) return MCTQ_E_BADARG;
     const IoSpan in[1] = {{a.x, (size_t)a.n * sizeof(T)}};
     const IoSpan out[2] = {{a.y, (size_t)a.n * sizeof(T)}, {a.codes, CODE == MCTQ_CODES_INT4 ? (size_t)(a.n + 1) / 2 : (size_t)a.n}};
-    a.early = (uint32_t)pdl_plan_launch(st, in, 1, out, CODE != 0 ? 2 : 1);
+    if (PREP && CHMODE != CH_PT) {
+        const IoSpan tables = {a.prep_flags, prep_bytes(a.C)};            // the blob starts with its flags word
+        a.early = (uint32_t)pdl_plan_launch(st, in, 1, out, CODE != 0 ? 2 : 1, &tables, &a.tab_early);
+        if (!a.tab_early) a.early = 0;
+    } else {
+        a.early = (uint32_t)pdl_plan_launch(st, in, 1, out, CODE != 0 ? 2 : 1);
+    }
     return launch_planned(fq_affine_kernel<T, CHMODE, CODE, UNROLL, RINT, PREP, VB>, (unsigned)tiles, smem, st, a);
 }
 
@@ -874,6 +895,7 @@ int mctq_affine_prepare(const float* scale, const int32_t* zp, int64_t C, void* 
     const int64_t C4 = (C + 3) & ~(int64_t)3;
     int64_t blocks = (C4 + kThreads - 1) / kThreads;
     if (blocks > 148 * 8) blocks = 148 * 8;
+    pdl_note_prepare(st, prepared_dev, prep_bytes(C));              // launches that follow stage this blob only after their wait
     affine_prepare_kernel<<<(unsigned)blocks, kThreads, 0, st>>>(scale, zp, C, C4, reinterpret_cast<uint8_t*>(prepared_dev));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cuda_rc(cudaGetLastError());

@@ -34,6 +34,7 @@ extern int g_wide;          // wide (8-element / 256-bit) vector variants (mctq_
 extern int g_multi_span;    // tiles per CTA of the multi-tensor LUT launch (mctq_set_tuning key 6)
 extern int g_lut_xy;        // xy-record variant of the prepared LUT kernel where it applies (mctq_set_tuning key 7)
 extern int g_pdl;           // programmatic dependent launch for the streaming kernels (mctq_set_tuning key 3)
+extern int g_tab_early;     // parameter tables staged before the dependent-launch wait when legal (mctq_set_tuning key 8)
 
 enum ChMode { CH_PT = 0, CH_VEC = 1, CH_ELEM = 2, CH_LAST = 3 };
 
@@ -282,7 +283,11 @@ __device__ __forceinline__ void pdl_exit(uint32_t order) {           // last sta
 // picks the most permissive order the new launch's ranges allow.  Launches whose ranges are not described (multi-tensor
 // plans) record "unknown", which forces the late order on their successor.
 struct IoSpan { const void* p; size_t bytes; };
-int pdl_plan_launch(cudaStream_t st, const IoSpan* in, int n_in, const IoSpan* out, int n_out);   // 0 late, 1 early, 2 free
+// `tables` (optional): the prepared blob the kernel stages into shared memory; *tab_early = 1 when it may do so before its wait
+int pdl_plan_launch(cudaStream_t st, const IoSpan* in, int n_in, const IoSpan* out, int n_out,    // 0 late, 1 early, 2 free
+                    const IoSpan* tables = nullptr, uint32_t* tab_early = nullptr);
+// a prepare kernel (plain launch: waits for everything before it) that writes `blob`
+void pdl_note_prepare(cudaStream_t st, const void* blob, size_t bytes);
 void pdl_forget_streams();                                           // every stream starts over with a late launch
 
 // ------------------------------------------------------------------------------------------ TMA bulk staging

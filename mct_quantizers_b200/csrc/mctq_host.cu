@@ -13,6 +13,7 @@ int g_pdl = 1;              // 0 off, 1 programmatic dependent launch (wait firs
 int g_lut_shfl = 1;
 int g_wide = 1;             // 8-element vectors / 256-bit stores where a kernel has them (key 5)
 int g_lut_xy = 1;           // key 7
+int g_tab_early = 1;        // key 8
 int g_multi_span = 4;       // tiles per CTA in the multi-tensor LUT launch: 1 or 4 (key 6; read when a plan is compiled)
 
 // ---- dependent-launch bookkeeping (see mctq_common.cuh): per (device, stream), the memory ranges of the library's launches
@@ -23,6 +24,7 @@ namespace {
 struct Span { uintptr_t lo, hi; };
 struct ChainLaunch {
     int n_in, n_out;        // -1 / -1: ranges unknown (multi-tensor plans): nothing may overlap with it
+    int prepare;            // a mctq_*_prepare kernel: its output is a parameter blob
     Span in[2], out[2];
 };
 constexpr int kChainMax = 3;             // a late launch + at most two launches that overlap with it, then a late one again
@@ -46,12 +48,15 @@ void pdl_forget_streams() {
     for (auto& c : g_chain) c.stamp = 0;
 }
 
-int pdl_plan_launch(cudaStream_t st, const IoSpan* in, int n_in, const IoSpan* out, int n_out) {
+static int plan_launch(cudaStream_t st, const IoSpan* in, int n_in, const IoSpan* out, int n_out, const IoSpan* tables, uint32_t* tab_early,
+                       int is_prepare) {
+    if (tab_early) *tab_early = 0;
     if (g_pdl == 0) return 0;
     int device = 0;
     if (cudaGetDevice(&device) != cudaSuccess) { cudaGetLastError(); return 0; }
     ChainLaunch me;
     me.n_in = me.n_out = -1;
+    me.prepare = is_prepare;
     if (in && out) {
         me.n_in = me.n_out = 0;
         for (int i = 0; i < n_in && i < 2; ++i)
@@ -83,6 +88,23 @@ int pdl_plan_launch(cudaStream_t st, const IoSpan* in, int n_in, const IoSpan* o
         }
         if (!unknown && !raw) order = (g_pdl >= 3 && !other && slot->n < kChainMax) ? 2 : 1;
     }
+    // Parameter tables (prepared blobs) are private to the library: only mctq_*_prepare writes them, and it declares the
+    // blob as its output here.  Unless such a launch is still in the chain, the tables were complete before the chain's
+    // first launch passed its wait, so a kernel may stage them BEFORE its own wait -- whatever other libraries enqueue
+    // on the stream (they never touch a blob), hence legal in the default mode too.  "Unknown" launches (multi-tensor
+    // plans) write tensors, never blobs.
+    if (tables && tab_early && g_tab_early && slot) {
+        // tables->p == nullptr: "several blobs" (multi-tensor plans) -- any prepare kernel in the chain counts
+        const Span t = {reinterpret_cast<uintptr_t>(tables->p), reinterpret_cast<uintptr_t>(tables->p) + tables->bytes};
+        bool fresh = false;
+        for (int k = 0; k < slot->n; ++k) {
+            const ChainLaunch& c = slot->l[k];
+            if (!c.prepare) continue;
+            if (!tables->p) fresh = true;
+            for (int j = 0; j < c.n_out; ++j) fresh |= overlaps(t, c.out[j]);
+        }
+        *tab_early = fresh ? 0u : 1u;
+    }
     // a stream this table has never seen (or whose entry was evicted): the predecessor may be one of our launches that
     // is no longer remembered -> late order
     if (!slot) { slot = victim; slot->n = 0; }
@@ -97,6 +119,16 @@ int pdl_plan_launch(cudaStream_t st, const IoSpan* in, int n_in, const IoSpan* o
         slot->n = 1;
     }
     return order;
+}
+
+int pdl_plan_launch(cudaStream_t st, const IoSpan* in, int n_in, const IoSpan* out, int n_out, const IoSpan* tables, uint32_t* tab_early) {
+    return plan_launch(st, in, n_in, out, n_out, tables, tab_early, 0);
+}
+
+void pdl_note_prepare(cudaStream_t st, const void* blob, size_t bytes) {
+    const IoSpan out[1] = {{blob, bytes}};
+    const IoSpan none[1] = {{nullptr, 0}};
+    plan_launch(st, none, 0, out, 1, nullptr, nullptr, 1);
 }
 }  // namespace mctq
 
@@ -122,6 +154,7 @@ int mctq_set_tuning(int key, int value) {
         case 4: prev = g_lut_shfl; g_lut_shfl = value ? 1 : 0; return prev;
         case 5: prev = g_wide; if (value < 0 || value > 2) return MCTQ_E_BADARG; g_wide = value; return prev;
         case 7: prev = g_lut_xy; g_lut_xy = value ? 1 : 0; return prev;
+        case 8: prev = g_tab_early; g_tab_early = value ? 1 : 0; pdl_forget_streams(); return prev;
         case 6: prev = g_multi_span; if (value != 1 && value != 4) return MCTQ_E_BADARG; g_multi_span = value; return prev;
         default: return MCTQ_E_BADARG;
     }

@@ -181,6 +181,7 @@ struct LutPArgs {
     FastDiv div_inner, div_W;
     uint32_t W, bigrow;
     uint32_t early;          // dependent-launch order: 0 late, 1 early, 2 free (opt-in, see pdl_plan_launch)
+    uint32_t tab_early;      // the tables may be staged before the dependent-launch wait (the blob is not being written)
 };
 
 __device__ __forceinline__ float fma_sat(float a, float b, float c) {
@@ -218,9 +219,43 @@ __device__ __forceinline__ void lutp_tile(const LutPArgs& a, const int64_t tile_
     const int64_t remaining = a.n - t0;
     const bool full = remaining >= (int64_t)TILE;
     const T* xt = reinterpret_cast<const T*>(a.x) + t0;
-    pdl_enter(a.early);
-    uint32_t tab_bytes = 0;                                           // bytes of FRONT in use: fetched while the tile loads are issued
-    if (tid == 0) tab_bytes = (uint32_t)__ldg(&reinterpret_cast<const LutPrepHeader*>(a.blob)->front_bytes);
+    // Stage the decision tables with the bulk-copy engine (1-D TMA): the blob already holds them in the layout the
+    // CTA wants -- [cells | orig] contiguous and channel records back to back -- so one elected thread arms the
+    // mbarrier and issues at most three cp.async.bulk copies (cells + orig, records c0 .. C-1, wrapped records 0 ..);
+    // they complete while every thread's streaming loads of the data tile are in flight.  When the host knows that the
+    // blob is not being written (tab_early) this happens BEFORE the dependent-launch wait: a CTA that was scheduled
+    // into the predecessor's tail has its tables in shared memory by the time the wait returns.
+    const uint32_t Wn = CHMODE == CH_PT ? 1u : a.W;
+    float* sm_rec = sm_dyn;
+    float* sm_front = sm_dyn + (size_t)Wn * a.rec_floats;             // consts | cq | orig | cells
+    auto stage = [&]() {
+        if (tid != 0) return;
+        const uint32_t tab_bytes = (uint32_t)__ldg(&reinterpret_cast<const LutPrepHeader*>(a.blob)->front_bytes);   // bytes of FRONT in use
+        mbar_init(&sm_bar, 1);
+        uint32_t c0 = 0;
+        if (CHMODE != CH_PT) {
+            const int64_t g0 = a.elem_offset + t0;
+            const int64_t r0 = g0 / a.inner;
+            const int64_t off = g0 - r0 * a.inner;
+            Window wv;
+            wv.off0 = a.bigrow ? 0u : (uint32_t)off;
+            const int64_t sp = a.inner - off;
+            wv.split = (uint32_t)(sp > (int64_t)TILE ? (int64_t)TILE + 1 : sp);
+            sm_win = wv;
+            c0 = (uint32_t)(r0 % a.C);
+        }
+        const uint32_t rec_bytes = (uint32_t)a.rec_floats * 4u;
+        const uint32_t n1 = min(Wn, (uint32_t)a.C - c0);            // records before the channel index wraps
+        mbar_arrive_expect_tx(&sm_bar, tab_bytes + Wn * rec_bytes);
+        bulk_g2s(sm_front, a.blob + a.off_front, tab_bytes, &sm_bar);
+        bulk_g2s(sm_rec, a.blob + a.off_rec + (size_t)c0 * rec_bytes, n1 * rec_bytes, &sm_bar);
+        if (n1 < Wn) bulk_g2s(reinterpret_cast<char*>(sm_rec) + (size_t)n1 * rec_bytes, a.blob + a.off_rec, (Wn - n1) * rec_bytes, &sm_bar);
+    };
+    // staging always precedes the tile loads (few registers are live here); what moves is the wait.  The host only picks
+    // an order other than "late" together with tab_early.
+    if (!a.tab_early) pdl_enter(0);
+    stage();
+    if (a.tab_early) pdl_enter(a.early);
 
     uint32_t w[UNROLL][WORDS_IN];
     if (full) {
@@ -241,35 +276,6 @@ __device__ __forceinline__ void lutp_tile(const LutPArgs& a, const int64_t tile_
     }
 
     pdl_loaded(a.early);                                                  // the tile is in flight; nothing is written before this point
-
-    // Stage the decision tables with the bulk-copy engine (1-D TMA): the blob already holds them in the layout the
-    // CTA wants -- [cells | orig] contiguous and channel records back to back -- so one elected thread arms the
-    // mbarrier and issues at most three cp.async.bulk copies (cells + orig, records c0 .. C-1, wrapped records 0 ..);
-    // they complete while every thread's streaming loads of the data tile are in flight.
-    const uint32_t Wn = CHMODE == CH_PT ? 1u : a.W;
-    float* sm_rec = sm_dyn;
-    float* sm_front = sm_dyn + (size_t)Wn * a.rec_floats;             // consts | cq | orig | cells
-    if (tid == 0) {
-        mbar_init(&sm_bar, 1);
-        uint32_t c0 = 0;
-        if (CHMODE != CH_PT) {
-            const int64_t g0 = a.elem_offset + t0;
-            const int64_t r0 = g0 / a.inner;
-            const int64_t off = g0 - r0 * a.inner;
-            Window wv;
-            wv.off0 = a.bigrow ? 0u : (uint32_t)off;
-            const int64_t sp = a.inner - off;
-            wv.split = (uint32_t)(sp > (int64_t)TILE ? (int64_t)TILE + 1 : sp);
-            sm_win = wv;
-            c0 = (uint32_t)(r0 % a.C);
-        }
-        const uint32_t rec_bytes = (uint32_t)a.rec_floats * 4u;
-        const uint32_t n1 = min(Wn, (uint32_t)a.C - c0);            // records before the channel index wraps
-        mbar_arrive_expect_tx(&sm_bar, tab_bytes + Wn * rec_bytes);
-        bulk_g2s(sm_front, a.blob + a.off_front, tab_bytes, &sm_bar);
-        bulk_g2s(sm_rec, a.blob + a.off_rec + (size_t)c0 * rec_bytes, n1 * rec_bytes, &sm_bar);
-        if (n1 < Wn) bulk_g2s(reinterpret_cast<char*>(sm_rec) + (size_t)n1 * rec_bytes, a.blob + a.off_rec, (Wn - n1) * rec_bytes, &sm_bar);
-    }
     __syncthreads();                                                  // barrier init + window visible to everyone
     Window win;
     if (CHMODE != CH_PT) win = sm_win;
@@ -485,9 +491,36 @@ __device__ __forceinline__ void lutx_tile(const LutPArgs& a, const int64_t tile_
     const int64_t remaining = a.n - t0;
     const bool full = remaining >= (int64_t)TILE;
     const T* xt = reinterpret_cast<const T*>(a.x) + t0;
-    pdl_enter(a.early);
-    uint32_t tab_bytes = 0;
-    if (tid == 0) tab_bytes = (uint32_t)__ldg(&reinterpret_cast<const LutPrepHeader*>(a.blob)->front_bytes);
+    const uint32_t Wn = CHMODE == CH_PT ? 1u : a.W;                   // channel slots (rows a tile can touch; <= kXyMaxW)
+    float* sm_rec = sm_dyn;
+    float* sm_front = sm_dyn + Wn * kXyRecFloats;
+    auto stage = [&]() {                                              // see lutp_tile: before the dependent-launch wait when legal
+        if (tid != 0) return;
+        const uint32_t tab_bytes = (uint32_t)__ldg(&reinterpret_cast<const LutPrepHeader*>(a.blob)->front_bytes);
+        mbar_init(&sm_bar, 1);
+        uint32_t c0 = 0;
+        if (CHMODE != CH_PT) {
+            const int64_t g0 = a.elem_offset + t0;
+            const int64_t r0 = g0 / a.inner;
+            const int64_t off = g0 - r0 * a.inner;
+            Window wv;
+            wv.off0 = a.bigrow ? 0u : (uint32_t)off;
+            const int64_t sp = a.inner - off;                         // elements of this tile in its first row
+            wv.split = (uint32_t)(sp > (int64_t)TILE ? (int64_t)TILE + 1 : sp);
+            sm_win = wv;
+            c0 = (uint32_t)(r0 % a.C);
+        }
+        const uint32_t n1 = min(Wn, (uint32_t)a.C - c0);              // records before the channel index wraps
+        mbar_arrive_expect_tx(&sm_bar, tab_bytes + Wn * REC);
+        bulk_g2s(sm_front, a.blob + a.off_front, tab_bytes, &sm_bar);
+        bulk_g2s(sm_rec, a.blob + a.off_xy + (size_t)c0 * REC, n1 * REC, &sm_bar);
+        if (n1 < Wn) bulk_g2s(reinterpret_cast<char*>(sm_rec) + (size_t)n1 * REC, a.blob + a.off_xy, (Wn - n1) * REC, &sm_bar);
+    };
+    // staging always precedes the tile loads (few registers are live here); what moves is the wait.  The host only picks
+    // an order other than "late" together with tab_early.
+    if (!a.tab_early) pdl_enter(0);
+    stage();
+    if (a.tab_early) pdl_enter(a.early);
 
     uint32_t w[UNROLL][WORDS_IN];
     if (full) {
@@ -508,30 +541,6 @@ __device__ __forceinline__ void lutx_tile(const LutPArgs& a, const int64_t tile_
     }
 
     pdl_loaded(a.early);                                                  // the tile is in flight; nothing is written before this point
-
-    const uint32_t Wn = CHMODE == CH_PT ? 1u : a.W;                   // channel slots (rows a tile can touch; <= kXyMaxW)
-    float* sm_rec = sm_dyn;
-    float* sm_front = sm_dyn + Wn * kXyRecFloats;
-    if (tid == 0) {
-        mbar_init(&sm_bar, 1);
-        uint32_t c0 = 0;
-        if (CHMODE != CH_PT) {
-            const int64_t g0 = a.elem_offset + t0;
-            const int64_t r0 = g0 / a.inner;
-            const int64_t off = g0 - r0 * a.inner;
-            Window wv;
-            wv.off0 = a.bigrow ? 0u : (uint32_t)off;
-            const int64_t sp = a.inner - off;                         // elements of this tile in its first row
-            wv.split = (uint32_t)(sp > (int64_t)TILE ? (int64_t)TILE + 1 : sp);
-            sm_win = wv;
-            c0 = (uint32_t)(r0 % a.C);
-        }
-        const uint32_t n1 = min(Wn, (uint32_t)a.C - c0);              // records before the channel index wraps
-        mbar_arrive_expect_tx(&sm_bar, tab_bytes + Wn * REC);
-        bulk_g2s(sm_front, a.blob + a.off_front, tab_bytes, &sm_bar);
-        bulk_g2s(sm_rec, a.blob + a.off_xy + (size_t)c0 * REC, n1 * REC, &sm_bar);
-        if (n1 < Wn) bulk_g2s(reinterpret_cast<char*>(sm_rec) + (size_t)n1 * REC, a.blob + a.off_xy, (Wn - n1) * REC, &sm_bar);
-    }
     __syncthreads();                                                  // barrier init + window visible to everyone
     Window win;
     if (CHMODE != CH_PT) win = sm_win;
@@ -724,10 +733,12 @@ int lutp_finish_args(LutPArgs& a, int chmode, int v, size_t* smem_out) {
 
 // declares the launch's inputs / outputs to the dependent-launch bookkeeping; 1 = the early order may be used
 template <typename T, int CODE>
-uint32_t lut_pdl_order(const LutPArgs& a, cudaStream_t st) {
+void lut_pdl_order(LutPArgs& a, cudaStream_t st) {
     const IoSpan in[1] = {{a.x, (size_t)a.n * sizeof(T)}};
     const IoSpan out[2] = {{a.y, (size_t)a.n * 4}, {a.idx, CODE == MCTQ_CODES_INT4 ? (size_t)(a.n + 1) / 2 : (size_t)a.n}};
-    return (uint32_t)pdl_plan_launch(st, in, 1, out, CODE != 0 ? 2 : 1);
+    const IoSpan tables = {a.blob, (size_t)a.off_rec + (size_t)a.C * a.rec_floats * 4 + (a.off_xy ? (size_t)a.C * kXyRecFloats * 4 : 0)};
+    a.early = (uint32_t)pdl_plan_launch(st, in, 1, out, CODE != 0 ? 2 : 1, &tables, &a.tab_early);
+    if (!a.tab_early) a.early = 0;         // tables after the wait: only the late order has that shape (right after a prepare call)
 }
 
 template <typename T, int CHMODE, int CODE, int V>
@@ -742,7 +753,7 @@ int launch_lutp_tiles(const LutPArgs& a_in, cudaStream_t st) {
     if (rc) return rc;
     int64_t tiles = (a.n + TILE - 1) / TILE;
     if (tiles > 0x7fffffffLL) return MCTQ_E_BADARG;
-    a.early = lut_pdl_order<T, CODE>(a, st);
+    lut_pdl_order<T, CODE>(a, st);
     return launch_planned(fq_lutp_kernel<T, CHMODE, CODE, UNROLL, V>, (unsigned)tiles, smem, st, a);
 }
 
@@ -770,7 +781,7 @@ int launch_lutx_tiles(const LutPArgs& a_in, cudaStream_t st) {
     if (rc) return rc;
     int64_t tiles = (a.n + TILE - 1) / TILE;
     if (tiles > 0x7fffffffLL) return MCTQ_E_BADARG;
-    a.early = lut_pdl_order<T, CODE>(a, st);
+    lut_pdl_order<T, CODE>(a, st);
     return launch_planned(fq_lutx_kernel<T, CHMODE, CODE, UNROLL, V>, (unsigned)tiles, smem, st, a);
 }
 
@@ -940,6 +951,7 @@ int mctq_lut_prepare(const void* table_host, int K, const float* thr_dev, int64_
     int64_t total = C * P;
     int64_t blocks = (total + kThreads - 1) / kThreads;
     if (blocks > 148 * 16) blocks = 148 * 16;
+    pdl_note_prepare(st, prepared_dev, g.bytes);                  // launches that follow stage this blob only after their wait
     lut_prepare_kernel<<<(unsigned)blocks, kThreads, 0, st>>>(reinterpret_cast<uint8_t*>(prepared_dev), thr_dev, eps, scalar_mode, divisor, thr_f32);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cuda_rc(cudaGetLastError());
@@ -982,7 +994,12 @@ int launch_multi_variant(const LutPMultiParams& c, size_t smem, cudaStream_t st)
     memcpy(p.e, c.e, (size_t)c.n_desc * sizeof(LutPMultiEntry));
     int rc = ensure_smem(fq_lut_multi_kernel<T, CHMODE, V, XY, CAP>, smem);
     if (rc) return rc;
-    return launch_streaming(fq_lut_multi_kernel<T, CHMODE, V, XY, CAP>, dim3((unsigned)c.tiles[kMultiMaxDesc], (unsigned)c.n_desc), smem, st, p);
+    // ranges "unknown" (late order); the tables of all tensors may be staged before the wait unless a prepare kernel is in flight
+    uint32_t te = 0;
+    const IoSpan any_blob = {nullptr, 0};
+    pdl_plan_launch(st, nullptr, 0, nullptr, 0, &any_blob, &te);
+    for (int i = 0; i < c.n_desc; ++i) p.e[i].a.tab_early = te;
+    return launch_planned(fq_lut_multi_kernel<T, CHMODE, V, XY, CAP>, dim3((unsigned)c.tiles[kMultiMaxDesc], (unsigned)c.n_desc), smem, st, p);
 }
 
 template <typename T, int CAP>

@@ -320,3 +320,62 @@ def test_private_stream_orders_respect_every_hazard_between_own_launches():
                     assert torch.equal(a, b), mode
         finally:
             lib.mctq_set_tuning(3, prev)
+
+
+def test_activation_quantizers_cut_the_autograd_graph_like_the_reference(Q):
+    """The reference runs torch.fake_quantize_per_tensor_affine under `with torch.no_grad():`
+    (activation_symmetric_inferable_quantizer.py:112, activation_uniform_inferable_quantizer.py:123), so its
+    activation quantizers return tensors that do NOT require grad even when the input does; the weights quantizers
+    clear `requires_grad` on their input (weights_symmetric_inferable_quantizer.py:138).  Same here, through the holder
+    (CUDA tensor: lean launch; torch.ops path: FakeTensor-visible operator)."""
+    from mct_quantizers_b200.pytorch.activation_quantization_holder import PytorchActivationQuantizationHolder
+    x = torch.randn(4, 33, device=DEV, requires_grad=True)
+    for q in (Q.ActivationSymmetricInferableQuantizer(8, [4.0], True), Q.ActivationPOTInferableQuantizer(8, [2.0], False),
+              Q.ActivationUniformInferableQuantizer(8, [-1.0], [2.3]),
+              Q.ActivationLutPOTInferableQuantizer(4, [-8.0, -2.0, 0.0, 3.0, 7.0], [2.0], True, 4, 1e-8)):
+        y = PytorchActivationQuantizationHolder(q)(x * 1.0)
+        assert not y.requires_grad and y.grad_fn is None
+    w = torch.nn.Parameter(torch.randn(8, 16, device=DEV))
+    yw = Q.WeightsSymmetricInferableQuantizer(8, [1.0] * 8, True, 0)(w)
+    assert not yw.requires_grad and not w.requires_grad
+
+
+@pytest.mark.parametrize("pdl_mode", [1, 2, 3])
+def test_tables_staged_before_the_wait_never_see_a_blob_being_prepared(Q, pdl_mode):
+    """Kernels stage their prepared parameter tables BEFORE the dependent-launch wait unless the blob was written by a
+    prepare call still in flight on the stream (mctq_set_tuning key 8).  Worst case for that rule: a long launch keeps
+    the GPU busy, a NEW quantizer is prepared (the allocator tends to hand out the address of the blob freed one
+    iteration earlier) and used at once -- a kernel that read the blob too early would see the previous iteration's
+    thresholds."""
+    from mct_quantizers_b200 import _native
+    lib = _native.load()
+    rng = np.random.default_rng(5)
+    busy = torch.empty(96 << 20, device=DEV).uniform_(-4, 4)
+    qa = Q.ActivationUniformInferableQuantizer(8, [-1.0], [2.0])
+    C, L = 256, 8192
+    w = torch.from_numpy(rng.standard_normal((C, L)).astype(np.float32)).to(DEV)
+    wb = w.to(torch.bfloat16)
+    lut = [-8.0, -5.0, -3.0, -1.0, 0.0, 1.0, 2.0, 4.0, 6.0, 7.0]
+    prev = lib.mctq_set_tuning(3, pdl_mode)
+    try:
+        for it in range(6):
+            thr = [float(v) for v in rng.uniform(0.5, 4.0, C)]
+            qa(busy)                                                     # ~100 us of work in front of the prepare
+            qs = Q.WeightsSymmetricInferableQuantizer(8, thr, True, 0)
+            ys = qs(w)
+            ys2 = qs(w)                                                  # second use: tables staged early
+            qa(busy)
+            ql = Q.WeightsLUTSymmetricInferableQuantizer(4, lut, thr, True, 0, 2, 4)
+            yl = ql(wb)
+            yl2 = ql(wb)
+            torch.cuda.synchronize()
+            want_s = _oracle_sym(w, thr)
+            assert G.bits_equal(ys.cpu().numpy(), np.asarray(want_s).reshape(ys.shape)), it
+            assert torch.equal(ys, ys2)
+            want_l = oracle.fq_lut(G.from_torch(wb), oracle.BF16, np.asarray(lut, np.float32), np.asarray(thr, np.float64).astype(np.float32),
+                                   C, L, 4, True, 1e-8)
+            assert G.bits_equal(yl.cpu().numpy(), np.asarray(want_l).reshape(yl.shape)), it
+            assert torch.equal(yl, yl2)
+            del qs, ql
+    finally:
+        lib.mctq_set_tuning(3, prev)
