@@ -292,7 +292,9 @@ int64_t mctq_launch_count(void);
  * key 7 = xy-record variant of the prepared LUT kernel for per-tensor / long-row launches (default 1),
  * key 8 = kernels stage their prepared parameter tables BEFORE the dependent-launch wait whenever the blob was not written by
  *   a prepare call still in flight on the stream (default 1; the blobs are private to the library, so this is legal whatever
- *   else runs on the stream);
+ *   else runs on the stream),
+ * key 9 = NVTX ranges (nvtx3, header-only) around every compute entry point, named after the entry point (default 0;
+ *   `ncu --nvtx` and timeline tools then attribute kernels to the call of the reference's API they belong to);
  * returns previous value or <0 */
 int mctq_set_tuning(int key, int value);
 /* device self-test of the 5-op correctly-rounded division used by the LUT kernels against __fdiv_rn

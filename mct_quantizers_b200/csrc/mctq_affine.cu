@@ -877,6 +877,7 @@ extern "C" {
 int mctq_fq_affine(const void* x, void* y, void* codes, int64_t n, int x_dtype, const float* scale, const int32_t* zp,
                    int64_t C, int64_t inner, int64_t elem_offset, int32_t qmin, int32_t qmax, int code_mode,
                    void* stream) {
+    MCTQ_NVTX("mctq_fq_affine");
     if (!scale || !zp) return MCTQ_E_BADARG;
     AffineArgs a;
     memset(&a, 0, sizeof(a));
@@ -888,6 +889,7 @@ int mctq_fq_affine(const void* x, void* y, void* codes, int64_t n, int x_dtype, 
 size_t mctq_affine_prepared_bytes(int64_t C) { return C < 1 ? 0 : prep_bytes(C); }
 
 int mctq_affine_prepare(const float* scale, const int32_t* zp, int64_t C, void* prepared_dev, size_t prepared_bytes, void* stream) {
+    MCTQ_NVTX("mctq_affine_prepare");
     if (!scale || !zp || !prepared_dev || C < 1 || prepared_bytes < prep_bytes(C) || !aligned16(prepared_dev)) return MCTQ_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(prepared_dev, 0, kPrepHeaderBytes, st);
@@ -903,6 +905,7 @@ int mctq_affine_prepare(const float* scale, const int32_t* zp, int64_t C, void* 
 
 int mctq_fq_affine_prepared(const void* x, void* y, void* codes, int64_t n, int x_dtype, const void* prepared_dev, int64_t C,
                             int64_t inner, int64_t elem_offset, int32_t qmin, int32_t qmax, int code_mode, void* stream) {
+    MCTQ_NVTX("mctq_fq_affine_prepared");
     if (!prepared_dev || C < 1 || !aligned16(prepared_dev)) return MCTQ_E_BADARG;
     const uint8_t* blob = reinterpret_cast<const uint8_t*>(prepared_dev);
     AffineArgs a;
@@ -921,6 +924,7 @@ int mctq_fq_affine_prepared(const void* x, void* y, void* codes, int64_t n, int 
 
 int mctq_fq_affine_scalar(const void* x, void* y, void* codes, int64_t n, int x_dtype, float scale, int32_t zp,
                           int32_t qmin, int32_t qmax, int code_mode, void* stream) {
+    MCTQ_NVTX("mctq_fq_affine_scalar");
     AffineArgs a;
     memset(&a, 0, sizeof(a));
     a.x = x; a.y = y; a.codes = codes; a.n = n; a.scale = nullptr; a.zp = nullptr; a.scale_val = scale; a.zp_val = zp;
@@ -930,6 +934,7 @@ int mctq_fq_affine_scalar(const void* x, void* y, void* codes, int64_t n, int x_
 
 int mctq_dequant_affine(const void* codes, int code_mode, int is_signed, float* y, int64_t n, const float* scale,
                         const int32_t* zp, int64_t C, int64_t inner, int64_t elem_offset, void* stream) {
+    MCTQ_NVTX("mctq_dequant_affine");
     if (!codes || !y || !scale || !zp || n < 0 || C < 1 || inner < 1) return MCTQ_E_BADARG;
     if (n == 0) return 0;
     if (code_mode != MCTQ_CODES_INT8 && code_mode != MCTQ_CODES_INT4) return MCTQ_E_BADARG;
@@ -984,12 +989,14 @@ int64_t mctq_multi_plan(const MctqTensorDesc* descs, int n_desc, int32_t* tile_s
 
 int mctq_fq_affine_multi(const MctqTensorDesc* descs_dev, const int32_t* tile_starts_dev, int n_desc,
                          int64_t total_tiles, void* stream) {
+    MCTQ_NVTX("mctq_fq_affine_multi");
     if (!descs_dev || !tile_starts_dev || n_desc < 1 || total_tiles < 0 || total_tiles > 0x7fffffffLL) return MCTQ_E_BADARG;
     if (total_tiles == 0) return 0;
     return launch_streaming(fq_affine_multi_kernel, (unsigned)total_tiles, 0, (cudaStream_t)stream, descs_dev, tile_starts_dev, n_desc);
 }
 
 int mctq_fq_affine_scalar_multi(const MctqSiteDesc* sites, int n_sites, void* stream) {
+    MCTQ_NVTX("mctq_fq_affine_scalar_multi");
     if (n_sites < 0 || (n_sites > 0 && !sites)) return MCTQ_E_BADARG;
     for (int k = 0; k < n_sites; ++k) {                     // validate everything before anything is launched
         const MctqSiteDesc& d = sites[k];

@@ -35,6 +35,7 @@ extern int g_multi_span;    // tiles per CTA of the multi-tensor LUT launch (mct
 extern int g_lut_xy;        // xy-record variant of the prepared LUT kernel where it applies (mctq_set_tuning key 7)
 extern int g_pdl;           // programmatic dependent launch for the streaming kernels (mctq_set_tuning key 3)
 extern int g_tab_early;     // parameter tables staged before the dependent-launch wait when legal (mctq_set_tuning key 8)
+extern int g_nvtx;          // NVTX ranges around the C-ABI compute entry points (mctq_set_tuning key 9 / MCTQ_TUNE=9=1; off by default)
 
 enum ChMode { CH_PT = 0, CH_VEC = 1, CH_ELEM = 2, CH_LAST = 3 };
 
@@ -317,6 +318,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ------------------------------------------------------------------------------------------ host helpers
+// NVTX (header-only v3: no link dependency; a no-op unless a profiler injected itself) -- one range per C-ABI call, named
+// after the entry point, so that an `ncu --nvtx` / Nsight Systems timeline shows which call of the reference's API a kernel
+// belongs to.  Costs one predictable branch when off.
+struct NvtxRange {
+    bool on;
+    explicit NvtxRange(const char* name);
+    ~NvtxRange();
+};
+#define MCTQ_NVTX(name) mctq::NvtxRange mctq_nvtx_range_(name)
 inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? 0 : (int)e; }
 
 // launch with the programmatic-serialization attribute; the caller has already declared the launch to pdl_plan_launch

@@ -160,6 +160,7 @@ extern "C" {
 
 int mctq_fq_affine_scalar_pre(const void* x, const void* x2, void* y, int64_t n, int x_dtype, int pre_op, float scale,
                               int32_t zp, int32_t qmin, int32_t qmax, void* stream) {
+    MCTQ_NVTX("mctq_fq_affine_scalar_pre");
     const bool two = pre_op == MCTQ_PRE_ADD || pre_op == MCTQ_PRE_ADD_RELU;
     if (!x || !y || n < 0 || (two && !x2) || pre_op < MCTQ_PRE_RELU || pre_op > MCTQ_PRE_ADD_RELU) return MCTQ_E_BADARG;
     if (qmin > qmax || !((int64_t)qmax - qmin < (1 << 21)) || zp < qmin || zp > qmax) return MCTQ_E_RANGE;

@@ -3,6 +3,7 @@
 #include <stdint.h>
 
 #include "mctq_common.cuh"
+#include <nvtx3/nvToolsExt.h>
 
 namespace mctq {
 std::atomic<int64_t> g_launches{0};
@@ -14,6 +15,7 @@ int g_lut_shfl = 1;
 int g_wide = 1;             // 8-element vectors / 256-bit stores where a kernel has them (key 5)
 int g_lut_xy = 1;           // key 7
 int g_tab_early = 1;        // key 8
+int g_nvtx = 0;             // key 9
 int g_multi_span = 4;       // tiles per CTA in the multi-tensor LUT launch: 1 or 4 (key 6; read when a plan is compiled)
 
 // ---- dependent-launch bookkeeping (see mctq_common.cuh): per (device, stream), the memory ranges of the library's launches
@@ -42,6 +44,9 @@ std::mutex g_chain_mu;
 
 inline bool overlaps(const Span& a, const Span& b) { return a.lo < b.hi && b.lo < a.hi; }
 }  // namespace
+
+NvtxRange::NvtxRange(const char* name) : on(g_nvtx != 0) { if (on) nvtxRangePushA(name); }
+NvtxRange::~NvtxRange() { if (on) nvtxRangePop(); }
 
 void pdl_forget_streams() {
     std::lock_guard<std::mutex> lock(g_chain_mu);
@@ -154,6 +159,7 @@ int mctq_set_tuning(int key, int value) {
         case 4: prev = g_lut_shfl; g_lut_shfl = value ? 1 : 0; return prev;
         case 5: prev = g_wide; if (value < 0 || value > 2) return MCTQ_E_BADARG; g_wide = value; return prev;
         case 7: prev = g_lut_xy; g_lut_xy = value ? 1 : 0; return prev;
+        case 9: prev = g_nvtx; g_nvtx = value ? 1 : 0; return prev;
         case 8: prev = g_tab_early; g_tab_early = value ? 1 : 0; pdl_forget_streams(); return prev;
         case 6: prev = g_multi_span; if (value != 1 && value != 4) return MCTQ_E_BADARG; g_multi_span = value; return prev;
         default: return MCTQ_E_BADARG;
@@ -360,6 +366,7 @@ int mctq_host_set_deferred(int device, int on) {
 }
 
 int mctq_host_wait(int device) {
+    MCTQ_NVTX("mctq_host_wait");
     HostCtx* ctx;
     int rc = host_ctx(device, &ctx);
     if (rc) return rc;
@@ -370,6 +377,7 @@ int mctq_host_wait(int device) {
 int mctq_fq_affine_host(const void* x_host, void* y_host, int64_t n, int x_dtype, const float* scale_host,
                         const int32_t* zp_host, int64_t C, int64_t inner, int32_t qmin, int32_t qmax,
                         void* staging_dev, size_t staging_bytes, int device) {
+    MCTQ_NVTX("mctq_fq_affine_host");
     if (!x_host || !y_host || !scale_host || !zp_host || !staging_dev || n < 0 || C < 1 || inner < 1) return MCTQ_E_BADARG;
     if (x_dtype < 0 || x_dtype > 2) return MCTQ_E_DTYPE;
     if (staging_bytes < mctq_host_staging_min_bytes() || (size_t)C * 4 > kRingArrayBytes) return MCTQ_E_BADARG;
@@ -407,6 +415,7 @@ int mctq_fq_affine_host(const void* x_host, void* y_host, int64_t n, int x_dtype
 int mctq_fq_lut_host(const void* x_host, float* y_host, int64_t n, int x_dtype, const void* table_host, int K,
                      const float* thr_host, int64_t C, int64_t inner, float eps, int scalar_mode, float divisor,
                      float thr_f32, int round_to_x_dtype, void* staging_dev, size_t staging_bytes, int device) {
+    MCTQ_NVTX("mctq_fq_lut_host");
     if (!x_host || !y_host || !table_host || !staging_dev || n < 0 || C < 1 || inner < 1) return MCTQ_E_BADARG;
     if (!scalar_mode && !thr_host) return MCTQ_E_BADARG;
     if (x_dtype < 0 || x_dtype > 2) return MCTQ_E_DTYPE;

@@ -857,6 +857,7 @@ size_t mctq_lut_prepared_bytes(int K, int lut_values_bitwidth, int is_signed, in
 
 int mctq_lut_prepare(const void* table_host, int K, const float* thr_dev, int64_t C, float eps, int scalar_mode,
                      float divisor, float thr_f32, int round_dtype, void* prepared_dev, size_t prepared_bytes, void* stream) {
+    MCTQ_NVTX("mctq_lut_prepare");
     if (!table_host || !prepared_dev || C < 1 || (!scalar_mode && !thr_dev) || round_dtype < 0 || round_dtype > 2) return MCTQ_E_BADARG;
     if (scalar_mode && C != 1) return MCTQ_E_BADARG;
     const LutTableHeader* th = reinterpret_cast<const LutTableHeader*>(table_host);
@@ -960,6 +961,7 @@ int mctq_lut_prepare(const void* table_host, int K, const float* thr_dev, int64_
 int mctq_fq_lut_prepared(const void* x, float* y, void* idx, int64_t n, int x_dtype, const void* prepared_dev, int K,
                          int lut_values_bitwidth, int is_signed, int64_t C, int64_t inner, int64_t elem_offset,
                          int idx_mode, void* stream) {
+    MCTQ_NVTX("mctq_fq_lut_prepared");
     LutPArgs a;
     int rc = lutp_make_args(x, y, idx, n, x_dtype, prepared_dev, K, lut_values_bitwidth, is_signed, C, inner, elem_offset, idx_mode, &a);
     if (rc) return rc;
@@ -1124,6 +1126,7 @@ int64_t mctq_lut_multi_plan(const MctqLutTensorDesc* descs, int n_desc, void* pl
 }
 
 int mctq_fq_lut_prepared_multi(const void* plan_host, void* stream) {
+    MCTQ_NVTX("mctq_fq_lut_prepared_multi");
     if (!plan_host) return MCTQ_E_BADARG;
     const LutPMultiHeader* h = reinterpret_cast<const LutPMultiHeader*>(plan_host);
     if (h->magic != kMultiMagic || h->n_desc < 1 || h->n_chunks < 1) return MCTQ_E_BADARG;

@@ -379,3 +379,19 @@ def test_tables_staged_before_the_wait_never_see_a_blob_being_prepared(Q, pdl_mo
             del qs, ql
     finally:
         lib.mctq_set_tuning(3, prev)
+
+
+def test_nvtx_ranges_can_be_switched_on():
+    """mctq_set_tuning key 9: NVTX ranges around the C-ABI entry points (no profiler attached here: the calls must be
+    harmless and the results unchanged)."""
+    from mct_quantizers_b200 import _native
+    lib = _native.load()
+    x = torch.randn(1 << 16, device=DEV)
+    q = __import__("mct_quantizers_b200.pytorch.quantizers", fromlist=["x"]).ActivationUniformInferableQuantizer(8, [-1.0], [2.0])
+    want = q(x)
+    prev = lib.mctq_set_tuning(9, 1)
+    try:
+        assert prev == 0
+        assert torch.equal(q(x), want)
+    finally:
+        assert lib.mctq_set_tuning(9, prev) == 1
