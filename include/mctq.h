@@ -210,8 +210,9 @@ int mctq_fq_lut_scalar(const void* x, float* y, void* idx, int64_t n, int x_dtyp
  *   table_host        the HOST copy of the blob from mctq_lut_build_table
  *   thr_dev           DEVICE f32 [C] (weights flavour) or NULL with scalar_mode = 1 (divisor / thr_f32 by value, C = 1)
  *   round_dtype       0 none; 1 / 2: the normalised value is rounded to bf16 / f16 first (activation flavour)
- *   prepared_dev      DEVICE buffer of mctq_lut_prepared_bytes(K, bw, signed, C) bytes (0 = configuration unsupported:
- *                     more than 4096 cells, i.e. lut_values_bitwidth > 10; use the generic entry points)
+ *   prepared_dev      DEVICE buffer of mctq_lut_prepared_bytes(K, bw, signed, C) bytes (0 = configuration unsupported)
+ * Grids of more than 10 bits use a cell table coarser than the integer grid; mctq_lut_prepare returns MCTQ_E_RANGE when the
+ * centroid list is too dense for it (two decision thresholds in one cell): use the generic entry points then.
  * mctq_lut_prepare is one-off setup and synchronises `stream` once.  mctq_fq_lut_prepared needs 16-byte aligned x / y and
  * returns MCTQ_E_RANGE when the channel window of a tile does not fit in shared memory (rows shorter than ~16
  * elements with large K): callers fall back to mctq_fq_lut. */
@@ -295,6 +296,7 @@ int64_t mctq_launch_count(void);
  *   else runs on the stream),
  * key 9 = NVTX ranges (nvtx3, header-only) around every compute entry point, named after the entry point (default 0;
  *   `ncu --nvtx` and timeline tools then attribute kernels to the call of the reference's API they belong to);
+ * key 10 = with key 3 = 3: how many launches may be in flight together before one waits again (2..8, default 3);
  * returns previous value or <0 */
 int mctq_set_tuning(int key, int value);
 /* device self-test of the 5-op correctly-rounded division used by the LUT kernels against __fdiv_rn

@@ -16,6 +16,7 @@ int g_wide = 1;             // 8-element vectors / 256-bit stores where a kernel
 int g_lut_xy = 1;           // key 7
 int g_tab_early = 1;        // key 8
 int g_nvtx = 0;             // key 9
+int g_chain_max = 3;        // key 10
 int g_multi_span = 4;       // tiles per CTA in the multi-tensor LUT launch: 1 or 4 (key 6; read when a plan is compiled)
 
 // ---- dependent-launch bookkeeping (see mctq_common.cuh): per (device, stream), the memory ranges of the library's launches
@@ -29,7 +30,7 @@ struct ChainLaunch {
     int prepare;            // a mctq_*_prepare kernel: its output is a parameter blob
     Span in[2], out[2];
 };
-constexpr int kChainMax = 3;             // a late launch + at most two launches that overlap with it, then a late one again
+constexpr int kChainMax = 8;             // capacity; g_chain_max (key 10) of them are used: a waiting launch + launches that overlap with it, then a waiting one again
 struct StreamChain {
     cudaStream_t st;
     int device;
@@ -91,7 +92,7 @@ static int plan_launch(cudaStream_t st, const IoSpan* in, int n_in, const IoSpan
                 for (int j = 0; j < c.n_in; ++j) other |= overlaps(me.out[i], c.in[j]);
             }
         }
-        if (!unknown && !raw) order = (g_pdl >= 3 && !other && slot->n < kChainMax) ? 2 : 1;
+        if (!unknown && !raw) order = (g_pdl >= 3 && !other && slot->n < g_chain_max) ? 2 : 1;
     }
     // Parameter tables (prepared blobs) are private to the library: only mctq_*_prepare writes them, and it declares the
     // blob as its output here.  Unless such a launch is still in the chain, the tables were complete before the chain's
@@ -159,6 +160,7 @@ int mctq_set_tuning(int key, int value) {
         case 4: prev = g_lut_shfl; g_lut_shfl = value ? 1 : 0; return prev;
         case 5: prev = g_wide; if (value < 0 || value > 2) return MCTQ_E_BADARG; g_wide = value; return prev;
         case 7: prev = g_lut_xy; g_lut_xy = value ? 1 : 0; return prev;
+        case 10: prev = g_chain_max; if (value < 2 || value > 8) return MCTQ_E_BADARG; g_chain_max = value; pdl_forget_streams(); return prev;
         case 9: prev = g_nvtx; g_nvtx = value ? 1 : 0; return prev;
         case 8: prev = g_tab_early; g_tab_early = value ? 1 : 0; pdl_forget_streams(); return prev;
         case 6: prev = g_multi_span; if (value != 1 && value != 4) return MCTQ_E_BADARG; g_multi_span = value; return prev;

@@ -43,9 +43,10 @@ struct LutPrepHeader {      // 96 bytes
     int32_t off_tau, off_front, off_rec, off_xy;   // byte offsets into the blob (off_xy == 0: no xy records)
     int32_t orig_identity;  // sorted position == original LUT index for every reachable position
     int32_t front_bytes;    // bytes of FRONT that are in use (multiple of 16)
-    int32_t cells_per_unit; // 1, 2 or 4
+    int32_t cells_per_unit; // 1, 2 or 4 ...
     float cell_offset;      // cells are shifted by this fraction of a cell against the integer grid
-    int32_t reserved[6];
+    int32_t cells_shift;    // ... divided by 2^cells_shift (grids of more than 10 bits: cells coarser than the integer grid)
+    int32_t reserved[5];
 };
 static_assert(sizeof(LutPrepHeader) == 96, "header layout");
 
@@ -55,16 +56,23 @@ struct PrepGeom {
     uint32_t rel_cq, rel_orig, rel_cells, front_cap;     // offsets inside FRONT; its capacity in bytes
 };
 
-static inline int64_t cells_needed(int cells_per_unit, int64_t mult) { return (int64_t)cells_per_unit * 2 * mult + 8; }
+static inline int64_t cells_needed(int cells_per_unit, int64_t mult, int shift = 0) { return (((int64_t)cells_per_unit * 2 * mult) >> shift) + 8; }
+constexpr int64_t kMaxCells = 4200;            // the byte-wide cell table has to fit comfortably in shared memory
+// smallest shift for which the finest geometry (kCellsPerUnitMax >> shift cells per step) fits: 0 for grids of <= 10 bits
+static inline int finest_shift(int64_t mult) {
+    int sh = 0;
+    while (cells_needed(kCellsPerUnitMax, mult, sh) > kMaxCells) ++sh;
+    return sh;
+}
 
 static int prep_geometry(int K, int bw, int is_signed, int64_t C, PrepGeom* g) {
     int L;
     if (lut_geometry_from_K(K, &g->P, &L)) return MCTQ_E_LUT;
     if (bw < 1 || bw > 16 || C < 1) return MCTQ_E_LUT;
     const int64_t mult = 1LL << (bw - (is_signed ? 1 : 0));
-    const int64_t nc = cells_needed(kCellsPerUnitMax, mult);
-    if (nc > 4200) return MCTQ_E_RANGE;           // table would not fit comfortably in shared memory
-    g->NC = (int)nc;
+    // grids of more than 10 bits: the cell grid is coarser than the integer grid (mctq_lut_prepare then checks that the
+    // centroid list is sparse enough for it and returns MCTQ_E_RANGE otherwise)
+    g->NC = (int)cells_needed(kCellsPerUnitMax, mult, finest_shift(mult));
     // everything the hot kernels stage with 16-byte bulk copies (FRONT, channel records) starts on a 16-byte boundary and
     // is a multiple of 16 bytes long, also for tables of one or two entries
     g->rec_floats = (g->P + 4 + 3) & ~3;
@@ -126,7 +134,7 @@ __global__ void __launch_bounds__(kThreads) lut_prepare_kernel(uint8_t* blob, co
         float* r = rec + c * h.rec_floats;
         if (j == 0) {
             // approximate cell scale: u = x * s' + 0.5, cell = round(u * NC)
-            r[h.P] = __fdiv_rn(__fmul_rn((float)h.cells_per_unit, h.mult), d) / (float)h.NC;
+            r[h.P] = __fdiv_rn(__fmul_rn(ldexpf((float)h.cells_per_unit, -h.cells_shift), h.mult), d) / (float)h.NC;   // power-of-two factors: exact
             r[h.P + 1] = t;                                                 // y = cq[pos] * thr_c (thr WITHOUT eps)
             r[h.P + 2] = d;
             if (xy) {
@@ -911,24 +919,40 @@ int mctq_lut_prepare(const void* table_host, int K, const float* thr_dev, int64_
     // shifted by a quarter cell so that neither integers nor half-integers sit on a cell boundary, is enough: 264 cells
     // for 8-bit grids instead of 2048 -- the byte-wide cell look-up then touches < 32 words for typical data and is all
     // but free of bank conflicts (ncu: 53-77 conflicts per 1000 elements with 2048 cells).
-    int cpu = kCellsPerUnitMax, NC = g.NC;
+    // Grids of more than 10 bits (round 2): the finest geometry that fits is COARSER than the integer grid (1 / 2^shift cells
+    // per step), so it is no longer valid for every centroid list -- lists whose thresholds are closer than a cell are
+    // refused (MCTQ_E_RANGE: the caller uses the generic kernel); k-means centroid lists on 12- or 16-bit grids are sparse
+    // and pass.  Candidates run from 16 x coarser than the finest to the finest.
+    const int sh0 = finest_shift((int64_t)th->mult);
+    struct Cand { int cpu, shift; };
+    std::vector<Cand> cands;
+    if (sh0 == 0) cands = {{1, 0}, {2, 0}, {kCellsPerUnitMax, 0}};
+    else for (int k = 4; k >= 0; --k) cands.push_back({kCellsPerUnitMax, sh0 + k});
+    int cpu = kCellsPerUnitMax, shift = 0, NC = g.NC;
     double off = 0.0;
+    bool found = false;
     std::vector<double> V(E.size());
-    for (int cand : {1, 2, kCellsPerUnitMax}) {
-        const int nc = (int)cells_needed(cand, (int64_t)th->mult);
-        const double o = cand < kCellsPerUnitMax ? 0.25 : 0.0;
+    for (const Cand& cand : cands) {
+        const bool finest = cand.cpu == kCellsPerUnitMax && cand.shift == sh0;
+        const int nc = (int)cells_needed(cand.cpu, (int64_t)th->mult, cand.shift);
+        if (nc < 40 && !finest) continue;
+        const double per_unit = std::ldexp((double)cand.cpu, -cand.shift);
+        const double o = (finest && sh0 == 0) ? 0.0 : 0.25;
         bool ok = true;
-        for (size_t j = 0; j < E.size(); ++j) V[j] = E[j] * (double)cand * (double)th->mult + 0.5 * nc + o;
+        for (size_t j = 0; j < E.size(); ++j) V[j] = E[j] * per_unit * (double)th->mult + 0.5 * nc + o;
         for (size_t j = 0; ok && j + 1 < E.size(); ++j) {
             if (!std::isfinite(V[j]) || !std::isfinite(V[j + 1])) continue;
             // two thresholds share a widened cell iff some integer k has k - 0.5 - slop <= V[j] and V[j + 1] <= k + 0.5 + slop
             const double k_lo = std::ceil(V[j + 1] - 0.5 - kCellSlop), k_hi = std::floor(V[j] + 0.5 + kCellSlop);
             if (k_lo <= k_hi) ok = false;
         }
-        if (ok || cand == kCellsPerUnitMax) { cpu = cand; NC = nc; off = o; break; }
+        // (4 cells per step of the integer grid are always valid: thresholds of integer centroids are >= half a step apart)
+        if (ok || (finest && sh0 == 0)) { cpu = cand.cpu; shift = cand.shift; NC = nc; off = o; found = true; break; }
     }
+    if (!found) return MCTQ_E_RANGE;
     h->NC = NC;
     h->cells_per_unit = cpu;
+    h->cells_shift = shift;
     h->cell_offset = (float)off;
     h->front_bytes = (int32_t)(g.rel_cells + (((uint32_t)NC + 1 + 15) & ~15u));
     float* consts = reinterpret_cast<float*>(front.data() + g.off_front);

@@ -491,7 +491,8 @@ def _table_on(table, device):
 
 def _prepared_for(table, K, device, thr_dev, eps, scalar, divisor, thr_f32, round_dtype):
     """Device blob of per-channel decision tables for this (centroid list, thresholds, device, rounding), built once.
-    None when the configuration is outside the prepared path (lut_values_bitwidth > 10, table not on the host)."""
+    None when the configuration is outside the prepared path (table not on the host; a grid of more than 10 bits with a
+    centroid list too dense for the cell table)."""
     if table.device.type != 'cpu':
         return None
     if scalar:
@@ -516,8 +517,11 @@ def _prepared_for(table, K, device, thr_dev, eps, scalar, divisor, thr_f32, roun
                 rc = lib.mctq_lut_prepare(_ptr(table), int(K), _ptr(thr_dev) if not scalar else None, C,
                                           float(np.float32(eps)), int(scalar), float(np.float32(divisor)),
                                           float(np.float32(thr_f32)), int(round_dtype), _ptr(blob), nbytes, _stream(device))
-            _native.check(rc, "mctq_lut_prepare")
-            torch.cuda.current_stream(device).synchronize()      # one-off: the blob may be used from any stream afterwards
+            if rc == -3:                                         # MCTQ_E_RANGE: a grid of more than 10 bits whose centroids are too
+                blob = None                                      # dense for the coarse cell table -> generic kernel
+            else:
+                _native.check(rc, "mctq_lut_prepare")
+                torch.cuda.current_stream(device).synchronize()  # one-off: the blob may be used from any stream afterwards
         hit = ((table, thr_dev), blob, bw, signed)
         _LUT_PREPARED[key] = hit
     return hit

@@ -30,9 +30,9 @@ class _Arrays:
 
 @lru_cache(maxsize=1)
 def _load():
-    """golden_v1 (make_golden.py) + golden_v2 (make_golden_v2.py): one manifest, one array lookup."""
+    """golden_v1 (make_golden.py) + golden_v2 (make_golden_v2.py) + golden_v3 (make_golden_v3.py): one manifest, one array lookup."""
     manifest, files = None, []
-    for stem in ("golden_v1", "golden_v2"):
+    for stem in ("golden_v1", "golden_v2", "golden_v3"):
         with open(os.path.join(HERE, "golden", stem + ".json")) as f:
             m = json.load(f)
         if manifest is None:

@@ -734,11 +734,12 @@ def test_first_lut_call_inside_a_graph_capture(Q):
 
 
 def test_lut_multi_plan_rejects_what_it_cannot_run(Q, lib):
-    """Tensors outside the prepared path (lut_values_bitwidth > 10, misaligned views) stay on their own call."""
+    """Tensors outside the prepared path (a centroid list too dense for the coarse cell table of a 14-bit grid, misaligned
+    views) stay on their own call."""
     from mct_quantizers_b200.pytorch.model_quantization import WeightPlan
-    lut = [float(v) for v in range(-2000, 2000, 250)]
+    lut = [-2000.0, -2.0, -1.0, 0.0, 1.0, 2.0, 1000.0, 2000.0]              # four thresholds inside one cell of the coarse table
     w = torch.randn(8, 256, device=DEV)
-    q_wide = Q.WeightsLUTSymmetricInferableQuantizer(4, lut, [1.0] * 8, True, 0, 2, 14)
+    q_wide = Q.WeightsLUTSymmetricInferableQuantizer(3, lut, [1.0] * 8, True, 0, 2, 14)
     base = torch.randn(8 * 256 + 1, device=DEV)
     w_mis = base[1:].view(8, 256)                                       # 4-byte aligned only
     q_ok = Q.WeightsLUTSymmetricInferableQuantizer(4, [float(v) for v in range(-128, 128, 16)], [1.0] * 8, True, 0, 2)
@@ -837,3 +838,50 @@ def test_model_weight_plan_hoists_weight_quantization(Q, lib):
         again = model(x)                                        # plan left: per-layer path is back
         assert lib.mctq_launch_count() - c0 == per_layer_launches
         assert torch.equal(again.view(torch.int32), want.view(torch.int32))
+
+
+@pytest.mark.parametrize("bw", [12, 14, 16])
+@pytest.mark.parametrize("dtype", ["float32", "bfloat16"])
+def test_wide_lut_grids_run_on_the_prepared_path(Q, bw, dtype):
+    """Grids of more than 10 bits: sparse centroid lists are served by the prepared kernels (cell table coarser than the
+    integer grid), values and packed 4-bit indices bit-equal to the oracle on a matrix large enough for the xy-record /
+    wide-vector variants; a list with neighbouring integers is refused by mctq_lut_prepare and runs on the generic kernel."""
+    from mct_quantizers_b200 import ops
+    rng = np.random.default_rng(bw)
+    lo, hi = -2 ** (bw - 1), 2 ** (bw - 1) - 1
+    lut = sorted(set(int(v) for v in rng.integers(lo, hi, size=16)) | {0})[:16]
+    while len(lut) < 16:
+        lut.append(lut[-1] + 7)
+    lut = [float(v) for v in lut if lo <= v <= hi]
+    C, L = 96, 4096
+    thr = [float(np.float32(v)) for v in rng.uniform(0.1, 4.0, C)]
+    w = torch.from_numpy(rng.standard_normal((C, L)).astype(np.float32)).to(DEV).to(G.TORCH_DT[dtype])
+    # plant points around every centroid midpoint of channel 0 and the last channel
+    for c in (0, C - 1):
+        mids = (np.asarray(lut[:-1]) + np.asarray(lut[1:])) / 2 / 2.0 ** (bw - 1) * (np.float32(thr[c]) + np.float32(1e-8))
+        pts = np.concatenate([np.nextafter(mids.astype(np.float32), np.float32(s)) for s in (-np.inf, np.inf)] + [mids.astype(np.float32)])
+        w[c, :pts.size] = torch.from_numpy(pts).to(w.dtype).to(DEV)
+    n0 = len(ops._LUT_PREPARED)
+    q = Q.WeightsLUTSymmetricInferableQuantizer(4, lut, thr, True, 0, 2, bw)
+    y = q(w)
+    new = [v for v in list(ops._LUT_PREPARED.values())[n0:]]
+    assert new and new[-1][1] is not None, "sparse list on a wide grid must be prepared"
+    want, want_idx = oracle.fq_lut(G.from_torch(w), G.DT_TAG[dtype], np.asarray(lut, np.float32), np.asarray(thr, np.float64).astype(np.float32),
+                                   C, L, bw, True, 1e-8, want_idx=True)
+    assert G.bits_equal(y.cpu().numpy(), np.asarray(want).reshape(y.shape))
+    from mct_quantizers_b200.pytorch.quantizer_utils import lut_search_table
+    table = lut_search_table(np.asarray(lut, np.float32), bw, True)
+    idx4 = torch.ops.mctq.lut_indices(w, table, len(lut), torch.tensor(thr, device=DEV), True, 0, 1e-8, 2).cpu().numpy()
+    un = np.stack([idx4 & 0xF, idx4 >> 4], 1).reshape(-1)[:w.numel()].astype(np.int32)
+    assert np.array_equal(un, np.asarray(want_idx).reshape(-1))
+    # dense list: refused by the prepared path, still exact
+    dense = [float(v) for v in (lo, -3, -2, -1, 0, 1, 900, hi)]           # five neighbouring integers
+    qd = Q.WeightsLUTSymmetricInferableQuantizer(3, dense, thr, True, 0, 2, bw)
+    n1 = len(ops._LUT_PREPARED)
+    yd = qd(w)
+    newd = list(ops._LUT_PREPARED.values())[n1:]
+    # 12 bits: one cell per grid step is still possible (valid for every integer list); beyond that the cells are wider
+    assert newd and (newd[-1][1] is None) == (bw > 12), "dense list on a 14- / 16-bit grid must fall back to the generic kernel"
+    wantd = oracle.fq_lut(G.from_torch(w), G.DT_TAG[dtype], np.asarray(dense, np.float32), np.asarray(thr, np.float64).astype(np.float32),
+                          C, L, bw, True, 1e-8)
+    assert G.bits_equal(yd.cpu().numpy(), np.asarray(wantd).reshape(yd.shape))

@@ -321,7 +321,8 @@ def test_lut_multi_plan_host_compiler():
     assert nb2 > nb
     # tensors the prepared path cannot run are refused (the caller keeps them on their own call)
     assert plan([desc(100, 4, 25, x=0x7f0000000004)])[1] == -1         # misaligned x
-    assert plan([desc(100, 4, 25, bw=14)])[1] == -3                    # lut_values_bitwidth > 10: cell table too large
+    assert plan([desc(100, 4, 25, bw=14)])[1] == 1                     # grids of more than 10 bits: coarse cell table (prepare decides)
+    assert plan([desc(100, 4, 25, bw=17)])[1] == -4                    # not a valid lut_values_bitwidth
     assert plan([desc(0, 1, 1)])[1] == -1                              # empty tensor
     assert plan([desc(100, 1, 1, dtype=5)])[1] == -2
     assert lib.mctq_fq_lut_prepared_multi(None, None) == -1
