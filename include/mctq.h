@@ -297,6 +297,8 @@ int64_t mctq_launch_count(void);
  * key 9 = NVTX ranges (nvtx3, header-only) around every compute entry point, named after the entry point (default 0;
  *   `ncu --nvtx` and timeline tools then attribute kernels to the call of the reference's API they belong to);
  * key 10 = with key 3 = 3: how many launches may be in flight together before one waits again (2..8, default 3);
+ * key 11 = data streams (= staging slots) of the host-buffer pipeline (2..6, default 3; mctq_host_staging_min_bytes follows),
+ * key 12 = number of chunks a tensor is cut into by the host-buffer pipeline in deferred mode (1..16, default 1: whole staging slots);
  * returns previous value or <0 */
 int mctq_set_tuning(int key, int value);
 /* device self-test of the 5-op correctly-rounded division used by the LUT kernels against __fdiv_rn

@@ -17,6 +17,8 @@ int g_lut_xy = 1;           // key 7
 int g_tab_early = 1;        // key 8
 int g_nvtx = 0;             // key 9
 int g_chain_max = 3;        // key 10
+int g_host_streams = 3;     // key 11: data streams (= staging slots) of the host-buffer pipeline
+int g_host_chunk_div_deferred = 1;   // key 12: a tensor is cut into about this many chunks in deferred mode (whole slots: measured best)
 int g_multi_span = 4;       // tiles per CTA in the multi-tensor LUT launch: 1 or 4 (key 6; read when a plan is compiled)
 
 // ---- dependent-launch bookkeeping (see mctq_common.cuh): per (device, stream), the memory ranges of the library's launches
@@ -160,6 +162,8 @@ int mctq_set_tuning(int key, int value) {
         case 4: prev = g_lut_shfl; g_lut_shfl = value ? 1 : 0; return prev;
         case 5: prev = g_wide; if (value < 0 || value > 2) return MCTQ_E_BADARG; g_wide = value; return prev;
         case 7: prev = g_lut_xy; g_lut_xy = value ? 1 : 0; return prev;
+        case 11: prev = g_host_streams; if (value < 2 || value > 6) return MCTQ_E_BADARG; g_host_streams = value; return prev;
+        case 12: prev = g_host_chunk_div_deferred; if (value < 1 || value > 16) return MCTQ_E_BADARG; g_host_chunk_div_deferred = value; return prev;
         case 10: prev = g_chain_max; if (value < 2 || value > 8) return MCTQ_E_BADARG; g_chain_max = value; pdl_forget_streams(); return prev;
         case 9: prev = g_nvtx; g_nvtx = value ? 1 : 0; return prev;
         case 8: prev = g_tab_early; g_tab_early = value ? 1 : 0; pdl_forget_streams(); return prev;
@@ -172,7 +176,7 @@ int mctq_set_tuning(int key, int value) {
 
 // ---------------------------------------------------------------------------------------------- host staging
 namespace {
-constexpr int kHostStreams = 3;
+constexpr int kHostStreams = 6;                      // capacity; g_host_streams of them are used (key 11)
 constexpr size_t kHostChunkBytesIn = 32u << 20;      // largest input chunk (slot size); small tensors use smaller chunks
 constexpr size_t kParamAreaBytes = 16u << 20;        // head of the staging buffer: parameters (device side)
 // The parameter area is a ring of kRing entries so that the uploads of call i + 1 never overwrite what the kernels of
@@ -184,7 +188,7 @@ constexpr size_t kRingTableBytes = 1u << 20;
 
 struct HostCtx {
     int device = -1;
-    cudaStream_t st[kHostStreams] = {nullptr, nullptr, nullptr};
+    cudaStream_t st[kHostStreams] = {};
     cudaStream_t st_par = nullptr;                   // parameter uploads: never queued behind a data chunk
     cudaEvent_t params_ready = nullptr;
     int deferred = 0;                                // calls return without synchronising (mctq_host_set_deferred)
@@ -241,10 +245,14 @@ int sync_all(HostCtx* ctx) {
 // chunk length: about an eighth of the tensor so that uploads, kernels and downloads of neighbouring chunks overlap
 // even for tensors of a few tens of MB, between 1 MB of input and the slot size, a multiple of 64 Ki elements
 // (a sixteenth was measured and is slower: 67 MB 76 -> 71 GB/s, the per-transfer latency of the copy engines dominates)
-int64_t pick_chunk_elems(int64_t n, size_t in_elem_bytes, size_t slot_elem_bytes) {
+// In deferred mode the pipeline does not drain between calls, so there is nothing to overlap WITHIN a tensor and whole
+// slots move best (divisor g_host_chunk_div_deferred, key 12, default 1): MobileNetV2 step with host tensors 87.2 GB/s with
+// eighths, 88.8 with halves, 91.6 with whole slots (6 streams instead of 3 on top: 92.2, not worth 300 MB of staging).
+int64_t pick_chunk_elems(int64_t n, size_t in_elem_bytes, size_t slot_elem_bytes, bool deferred) {
     const int64_t max_elems = (int64_t)(kHostChunkBytesIn / slot_elem_bytes);
     const int64_t min_elems = (int64_t)((1u << 20) / in_elem_bytes);
-    int64_t c = (n / 8 + 65535) / 65536 * 65536;
+    const int64_t div = deferred ? g_host_chunk_div_deferred : 8;
+    int64_t c = (n / div + 65535) / 65536 * 65536;
     if (c < min_elems) c = min_elems;
     if (c > max_elems) c = max_elems;
     return c;
@@ -308,9 +316,9 @@ struct HostCall {
     int run(const uint8_t* x_host, uint8_t* y_host, int64_t n, size_t in_es, size_t out_es, bool zero_copy, Launch launch) {
         cudaError_t e = cudaSuccess;
         int rc = 0;
-        bool used[kHostStreams] = {false, false, false};
+        bool used[kHostStreams] = {};
         auto stream_for = [&](uint64_t k) {
-            const int i = (int)(k % kHostStreams);
+            const int i = (int)(k % (uint64_t)g_host_streams);
             if (!used[i]) {
                 used[i] = true;
                 if (entry >= 0) cudaStreamWaitEvent(ctx->st[i], ctx->params_ready, 0);
@@ -323,7 +331,7 @@ struct HostCall {
             rc = launch(x_host, y_host, n, 0, ctx->st[i]);
         } else {
             uint8_t* slots = base + kParamAreaBytes;
-            const int64_t chunk_elems = pick_chunk_elems(n, in_es, in_es > out_es ? in_es : out_es);
+            const int64_t chunk_elems = pick_chunk_elems(n, in_es, in_es > out_es ? in_es : out_es, ctx->deferred != 0);
             for (int64_t off = 0; off < n; off += chunk_elems) {
                 const int64_t cnt = (n - off) < chunk_elems ? (n - off) : chunk_elems;
                 const int i = stream_for(ctx->next_chunk++);
@@ -354,7 +362,7 @@ extern "C" {
 
 size_t mctq_host_staging_min_bytes(void) {
     // per stream: one input chunk + one f32-sized output chunk (LUT output of a 2-byte input is 2x larger) + parameter area
-    return kHostStreams * (kHostChunkBytesIn + 2 * kHostChunkBytesIn) + kParamAreaBytes;
+    return (size_t)g_host_streams * (kHostChunkBytesIn + 2 * kHostChunkBytesIn) + kParamAreaBytes;
 }
 
 int mctq_host_set_deferred(int device, int on) {

@@ -194,8 +194,8 @@ _staging = {}
 
 def _staging_buffer(device_index):
     buf = _staging.get(device_index)
-    if buf is None:
-        nbytes = _native.load().mctq_host_staging_min_bytes()
+    nbytes = _native.load().mctq_host_staging_min_bytes()        # depends on the number of pipeline streams (tuning key 11)
+    if buf is None or buf.numel() < nbytes:
         buf = torch.empty(nbytes, dtype=torch.uint8, device=torch.device("cuda", device_index))
         _staging[device_index] = buf
     return buf
