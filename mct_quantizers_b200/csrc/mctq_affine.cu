@@ -793,6 +793,8 @@ int launch_affine_unroll(const AffineArgs& a, cudaStream_t st) {
     if (CODE == MCTQ_CODES_NONE && !RINT) {
         // automatic: 8 KB tiles for per-tensor launches (nothing to stage per tile; tools/stream_probe.cu measures
         // +2 % over 16 KB tiles), 16 KB tiles when a channel window is staged per tile
+        // (4 KB tiles were measured in round 2 and are slower at every size: 74 MB 5.72 -> 5.16 TB/s queued, 295 MB 6.63 ->
+        // 5.94, 1 GB 6.91 -> 6.16 for bf16; the ~3 us a mid-size launch loses are drain + ramp, not tile granularity)
         const int u = g_unroll ? g_unroll : (CHMODE == CH_PT ? 2 : 4);
         if (u == 2) return launch_affine_tiles<T, CHMODE, MCTQ_CODES_NONE, 2, false>(a, st);
         if (u == 8) return launch_affine_tiles<T, CHMODE, MCTQ_CODES_NONE, 8, false>(a, st);
