@@ -178,3 +178,42 @@ def test_c5_16gb_f32_point(Q):
         del y
     del x
     torch.cuda.empty_cache()
+
+
+def test_lut_beyond_2_31_elements(Q):
+    """LUT quantizers on 2^31 + 2^20 + 4099 bf16 elements in ONE call (4 GiB in, 8 GiB of f32 out): 64-bit tile indexing of the
+    prepared LUT kernels -- the per-tensor activation flavour (every eager op rounds to bf16) and per-channel weights with
+    rows of 2^20 elements (channel = tile_start / inner in 64-bit arithmetic)."""
+    n = (1 << 31) + (1 << 20) + 4096 + 3
+    free, _ = torch.cuda.mem_get_info()
+    if free < n * 2 + n * 4 + (6 << 30):
+        pytest.skip("not enough free device memory")
+    g = torch.Generator(device=DEV).manual_seed(31)
+    x = torch.empty(n, device=DEV, dtype=torch.bfloat16)
+    step = 1 << 28
+    for s in range(0, n, step):
+        x[s:s + step].uniform_(-3, 3, generator=g)
+    lut = [-128.0, -100.0, -64.0, -30.0, -9.0, 0.0, 7.0, 21.0, 50.0, 90.0, 127.0]
+    qa = Q.ActivationLutPOTInferableQuantizer(4, lut, [2.0], True)
+    y = qa(x)
+    assert y.dtype == torch.float32 and y.numel() == n
+    for lo in (0, (1 << 30) - 33333, (1 << 31) - 30000, n - 60000):
+        hi = min(lo + 60000, n)
+        want = oracle.fq_lut(_bits(x[lo:hi]), oracle.BF16, np.asarray(lut, np.float32), 2.0, 1, 1, 8, True, 1e-8, activation_mode=True)
+        assert G.bits_equal(y[lo:hi].cpu().numpy(), np.asarray(want).reshape(-1)), lo
+    del y
+    torch.cuda.empty_cache()
+    # per-channel weights: 2049 rows of 2^20 elements (the tail of x is left out)
+    C, L = 2049, 1 << 20
+    rng = np.random.default_rng(2049)
+    thr = [float(np.float32(v)) for v in rng.uniform(0.5, 3.0, C)]
+    w = x[:C * L].view(C, L)
+    qw = Q.WeightsLUTSymmetricInferableQuantizer(4, lut, thr, True, 0, 2)
+    yw = qw(w)
+    thr32 = np.asarray(thr, np.float64).astype(np.float32)
+    for c in (0, 1023, 1024, 2047, 2048):
+        for lo in (0, L - 4096):
+            want = oracle.fq_lut(_bits(w[c, lo:lo + 4096]), oracle.BF16, np.asarray(lut, np.float32), thr32[c:c + 1], 1, 4096, 8, True, 1e-8)
+            assert G.bits_equal(yw[c, lo:lo + 4096].cpu().numpy(), np.asarray(want).reshape(-1)), (c, lo)
+    del yw, w, x
+    torch.cuda.empty_cache()
