@@ -15,8 +15,9 @@ absmax), every ReLU / ReLU6 is followed by a `PytorchActivationQuantizationHolde
   b200+plan        + `plan_model_weights(model).enable()`: all weights quantized by ONE launch, wrappers skip theirs
   b200+plan+fuse   + `fuse_activation_producers(model)`: ReLU / ReLU6 run inside the holder's kernel
 
-Reported per arm and batch: milliseconds per forward (CUDA events, median) and, for batch 1, wall-clock per forward with
-the queue drained (host-bound regime); outputs of every arm are compared with the reference arm's.  Convolutions are
+Reported per arm and batch: milliseconds per forward (CUDA events, median), for batch 1 wall-clock per forward with the
+queue drained (host-bound regime), for batches <= 32 the replay time of the forward captured in a CUDA graph (the
+reference cannot be captured); outputs of every arm are compared with the reference arm's.  Convolutions are
 the same cuDNN kernels in every arm, so the differences are the fake-quant path and its host side.
 """
 import argparse
@@ -79,6 +80,30 @@ def wall_ms(fn, reps):
     return (time.perf_counter() - t0) / reps * 1e3
 
 
+def graph_replay_ms(model, x, want):
+    """Capture one forward in a CUDA graph and time replays.  The reference cannot be captured: its per-channel weights path
+    reads scale / zero point back to the host (`.item()`) inside every forward."""
+    try:
+        with torch.no_grad():
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(2):
+                    model(x)
+            torch.cuda.current_stream().wait_stream(s)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                y = model(x)
+            g.replay()
+            torch.cuda.synchronize()
+            ok = bool(torch.equal(y, want))
+            ms = events_ms(g.replay, 30)
+        return round(ms, 4), ("replay == eager" if ok else "replay DIFFERS from eager")
+    except Exception as e:          # noqa: BLE001 -- reported, not hidden
+        torch.cuda.synchronize()
+        return None, "not capturable (" + str(e).split("\n")[0][:90] + ")"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--json", default=None)
@@ -126,13 +151,16 @@ def main():
                     reps = 30 if batch <= 32 else 10
                     ms = events_ms(lambda: model(x), reps)
                     wall = wall_ms(lambda: model(x), 20) if batch == 1 else None
+                graph_ms, graph_note = graph_replay_ms(model, x, want) if batch <= 32 else (None, None)
                 row = {"model": mname, "batch": batch, "arm": arm, "ms_per_forward": round(ms, 4),
+                       "cuda_graph_ms": graph_ms, "cuda_graph_note": graph_note,
                        "wall_ms_batch1": None if wall is None else round(wall, 4), "bit_equal_to_reference": same,
                        "max_abs_diff": maxdiff, "wrapped_layers": n_w, "holders": n_h}
                 rows.append(row)
                 print(f"{mname:13s} batch {batch:4d}  {arm:15s} {ms:9.3f} ms / forward" +
                       (f"  (wall, drained queue: {wall:7.3f} ms)" if wall is not None else "") +
-                      f"  equal={same} maxdiff={maxdiff:.3g}", flush=True)
+                      f"  equal={same} maxdiff={maxdiff:.3g}" +
+                      ("" if graph_note is None else f"  | CUDA graph: {graph_note if graph_ms is None else f'{graph_ms:.3f} ms / replay'}"), flush=True)
         del plan, plan2
     if args.json:
         with open(args.json, "w") as f:
