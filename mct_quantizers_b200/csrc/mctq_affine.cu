@@ -38,6 +38,9 @@ struct AffineArgs {
 constexpr size_t kPrepHeaderBytes = 16;
 inline size_t prep_bytes(int64_t C) { int64_t C4 = (C + 3) & ~(int64_t)3; return kPrepHeaderBytes + (size_t)C * 16 + (size_t)C4 * 12; }
 
+// (float)k for |k| < 2^22 without I2F (a quarter-rate conversion): the mantissa of 1.5 * 2^23 + k holds k
+__device__ __forceinline__ float small_int_to_float(int k) { return __fsub_rn(__int_as_float(0x4B400000 + k), kMagic); }
+
 template <bool RINT> struct AffineOp {
     using Args = AffineArgs;
     struct ChanParams { float inv, s, lo, hi; int zp; };
@@ -49,7 +52,7 @@ template <bool RINT> struct AffineOp {
         p.inv = __fdiv_rn(1.0f, s);                  // IEEE reciprocal of the f32 scale (ATen: 1.0f / scale)
         p.zp = zp;
         if (RINT) { p.lo = (float)a.qmin; p.hi = (float)a.qmax; }
-        else { p.lo = (float)(a.qmin - zp); p.hi = (float)(a.qmax - zp); }
+        else { p.lo = small_int_to_float(a.qmin - zp); p.hi = small_int_to_float(a.qmax - zp); }    // |q - zp| <= 2^21 on this path
         return p;
     }
     __device__ static __forceinline__ ChanParams uniform(const Args& a) {
@@ -69,7 +72,7 @@ template <bool RINT> struct AffineOp {
         p.s = sm[W + slot];
         p.zp = __float_as_int(sm[2 * W + slot]);
         if (RINT) { p.lo = (float)a.qmin; p.hi = (float)a.qmax; }
-        else { p.lo = (float)(a.qmin - p.zp); p.hi = (float)(a.qmax - p.zp); }
+        else { p.lo = small_int_to_float(a.qmin - p.zp); p.hi = small_int_to_float(a.qmax - p.zp); }
         return p;
     }
     // prepared record {1/s, s, zp bits, (float)zp}: one 16-byte shared-memory load, no int -> float conversions
@@ -95,7 +98,9 @@ template <bool RINT> struct AffineOp {
             // r to [qmin - zp, qmax - zp] equals clamp(r + zp, qmin, qmax) - zp on integer-valued floats.
             float r = __fsub_rn(__fadd_rn(t, kMagic), kMagic);
             float c = fminf(fmaxf(r, p.lo), p.hi);           // fmaxf(NaN, lo) = lo: NaN -> qmin
-            if (WANT_CODE) code = (int)c + p.zp;
+            // integer code without F2I (a quarter-rate conversion that made the codes-only bf16 variant issue bound): c is an
+            // integer with |c| < 2^22, so the low mantissa bits of c + 1.5 * 2^23 ARE c in two's complement
+            if (WANT_CODE) code = __float_as_int(__fadd_rn(c, kMagic)) + (p.zp - 0x4B400000);
             return __fmul_rn(c, p.s);
         } else {
             float zf = (float)p.zp;
@@ -258,7 +263,7 @@ __global__ void __launch_bounds__(kThreads) fq_affine_kernel(const AffineArgs a)
                     p.s = ps[e];
                     p.zp = __float_as_int(pz[e]);
                     if (RINT) { p.lo = (float)a.qmin; p.hi = (float)a.qmax; }
-                    else { p.lo = (float)(a.qmin - p.zp); p.hi = (float)(a.qmax - p.zp); }
+                    else { p.lo = small_int_to_float(a.qmin - p.zp); p.hi = small_int_to_float(a.qmax - p.zp); }
                     f[e] = Op::template apply<CODE != 0>(f[e], p, code[e]);
                 }
             }
