@@ -72,7 +72,10 @@ const char* mctq_build_info(void);
  * x, y       device, n elements of x_dtype; y may be NULL when only codes are wanted
  * codes      device or NULL; layout per code_mode
  * scale, zp  device arrays of C entries (read on the device: no host sync, unlike the reference's
- *            per-channel path which does two .item() round trips per call)
+ *            per-channel path which does two .item() round trips per call).  ATen rejects per-channel zero points
+ *            outside [qmin, qmax]; this entry point cannot look (no sync) and only needs |q - zp[c]| < 2^22 for every
+ *            q in [qmin, qmax] when qmax - qmin < 2^21 (the fast-rounding path); the Python quantizers check the range on
+ *            the host at construction time and raise ATen's error.
  */
 int mctq_fq_affine(const void* x, void* y, void* codes, int64_t n, int x_dtype,
                    const float* scale, const int32_t* zp, int64_t C, int64_t inner, int64_t elem_offset,
