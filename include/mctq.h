@@ -200,6 +200,10 @@ int mctq_fq_lut(const void* x, float* y, void* idx, int64_t n, int x_dtype,
  * d = (float)(thr + eps) computed in double by the caller and passed by value with thr_f32 = (float)thr;
  * for bf16/f16 inputs the reference's eager ops round the normalised value back to the input dtype
  * before the search (round_to_x_dtype = 1). */
+#define MCTQ_LUT_DIVISOR_IS_MULTIPLIER 2   /* OR into round_to_x_dtype: `divisor` is r = (float)(1.0 / (thr + eps)) and the
+                                            * normalisation is x * r -- what libtorch's CUDA kernel for `tensor / python_number`
+                                            * computes, i.e. what the unmodified reference yields for CUDA tensors (it differs from
+                                            * the CPU kernel's true division at rounding ties).  mctq_lut_prepare: scalar_mode = 2 */
 int mctq_fq_lut_scalar(const void* x, float* y, void* idx, int64_t n, int x_dtype,
                        const void* table_dev, int K, float divisor, float thr_f32, int round_to_x_dtype,
                        int idx_mode, void* stream);

@@ -21,3 +21,4 @@ from mct_quantizers_b200.pytorch import quantizers as pytorch_quantizers
 from mct_quantizers_b200.pytorch.fused_activation_holder import PytorchFusedActivationQuantizationHolder, \
     fuse_activation_producers
 from mct_quantizers_b200.ops import host_pipeline, private_stream
+from mct_quantizers_b200.pytorch.quantizer_utils import reference_arithmetic

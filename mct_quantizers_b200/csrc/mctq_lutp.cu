@@ -134,7 +134,8 @@ __global__ void __launch_bounds__(kThreads) lut_prepare_kernel(uint8_t* blob, co
         float* r = rec + c * h.rec_floats;
         if (j == 0) {
             // approximate cell scale: u = x * s' + 0.5, cell = round(u * NC)
-            r[h.P] = __fdiv_rn(__fmul_rn(ldexpf((float)h.cells_per_unit, -h.cells_shift), h.mult), d) / (float)h.NC;   // power-of-two factors: exact
+            const float cm = __fmul_rn(ldexpf((float)h.cells_per_unit, -h.cells_shift), h.mult);       // power-of-two factors: exact
+            r[h.P] = (scalar_mode == 2 ? __fmul_rn(cm, d) : __fdiv_rn(cm, d)) / (float)h.NC;
             r[h.P + 1] = t;                                                 // y = cq[pos] * thr_c (thr WITHOUT eps)
             r[h.P + 2] = d;
             if (xy) {
@@ -152,7 +153,8 @@ __global__ void __launch_bounds__(kThreads) lut_prepare_kernel(uint8_t* blob, co
             if (tj == -INFINITY) X = -INFINITY;
             else if (tj != INFINITY) {
                 // P(x) := round_like(x / d) > tau_j is monotone in x (d > 0); X = largest x for which it is false
-                auto above = [&](float x) { return round_like(__fdiv_rn(x, d), h.round_dtype) > tj; };
+                // scalar_mode 2: d is the multiplier f32(1 / (thr + eps)) of the reference's CUDA flavour (monotone as well)
+                auto above = [&](float x) { return round_like(scalar_mode == 2 ? __fmul_rn(x, d) : __fdiv_rn(x, d), h.round_dtype) > tj; };
                 const float big = 3.4028234663852886e38f;
                 if (above(-big)) X = -INFINITY;
                 else if (!above(big)) X = big;
@@ -866,7 +868,7 @@ size_t mctq_lut_prepared_bytes(int K, int lut_values_bitwidth, int is_signed, in
 int mctq_lut_prepare(const void* table_host, int K, const float* thr_dev, int64_t C, float eps, int scalar_mode,
                      float divisor, float thr_f32, int round_dtype, void* prepared_dev, size_t prepared_bytes, void* stream) {
     MCTQ_NVTX("mctq_lut_prepare");
-    if (!table_host || !prepared_dev || C < 1 || (!scalar_mode && !thr_dev) || round_dtype < 0 || round_dtype > 2) return MCTQ_E_BADARG;
+    if (!table_host || !prepared_dev || C < 1 || (!scalar_mode && !thr_dev) || round_dtype < 0 || round_dtype > 2 || scalar_mode < 0 || scalar_mode > 2) return MCTQ_E_BADARG;
     if (scalar_mode && C != 1) return MCTQ_E_BADARG;
     const LutTableHeader* th = reinterpret_cast<const LutTableHeader*>(table_host);
     if (th->magic != kLutMagic || th->K != K) return MCTQ_E_LUT;

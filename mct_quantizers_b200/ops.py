@@ -29,7 +29,7 @@ _LIB.define("fq_affine_scalar_pre(Tensor x, Tensor? other, int pre_op, float sca
 _LIB.define("fq_affine_tensor(Tensor x, Tensor scale, Tensor zero_point, int quant_min, int quant_max) -> Tensor")
 _LIB.define("fq_affine_channel(Tensor x, Tensor scale, Tensor zero_point, int axis, int quant_min, int quant_max) -> Tensor")
 _LIB.define("fq_lut_tensor(Tensor x, Tensor table, int K, Tensor threshold, bool per_channel, int axis, float eps) -> Tensor")
-_LIB.define("fq_lut_scalar(Tensor x, Tensor table, int K, float divisor, float threshold, bool round_to_input_dtype) -> Tensor")
+_LIB.define("fq_lut_scalar(Tensor x, Tensor table, int K, float divisor, float threshold, bool round_to_input_dtype, bool multiply=False) -> Tensor")
 _LIB.define("quantize_affine_channel(Tensor x, Tensor scale, Tensor zero_point, int axis, int quant_min, int quant_max, "
             "int code_mode, bool want_values) -> (Tensor, Tensor)")
 _LIB.define("dequantize_affine(Tensor codes, int code_mode, bool is_signed, int[] shape, Tensor scale, Tensor zero_point, "
@@ -496,7 +496,7 @@ def _prepared_for(table, K, device, thr_dev, eps, scalar, divisor, thr_f32, roun
     if table.device.type != 'cpu':
         return None
     if scalar:
-        key = (table.data_ptr(), int(K), str(device), 's', float(divisor), float(thr_f32), int(round_dtype))
+        key = (table.data_ptr(), int(K), str(device), 's', int(scalar), float(divisor), float(thr_f32), int(round_dtype))
         C = 1
     else:
         key = (table.data_ptr(), int(K), str(device), 't', thr_dev.data_ptr(), _ver(thr_dev), thr_dev.numel(), float(eps))
@@ -545,7 +545,8 @@ def _lut_launch(xd, y, idx, idx_mode, table, K, C, inner, thr_dev, eps, scalar, 
         t = _table_on(table, xd.device)
         if scalar:
             rc = lib.mctq_fq_lut_scalar(_ptr(xd), _ptr(y), _ptr(idx), n, tag, _ptr(t), int(K), float(np.float32(divisor)),
-                                        float(np.float32(thr_f32)), int(bool(round_flag)), int(idx_mode), _stream(xd.device))
+                                        float(np.float32(thr_f32)), int(bool(round_flag)) | (2 if scalar == 2 else 0), int(idx_mode),
+                                        _stream(xd.device))
         else:
             rc = lib.mctq_fq_lut(_ptr(xd), _ptr(y), _ptr(idx), n, tag, _ptr(t), int(K), _ptr(thr_dev), C, inner, 0,
                                  float(np.float32(eps)), int(idx_mode), _stream(xd.device))
@@ -631,12 +632,17 @@ def _lut_indices_cuda(x, table, K, threshold, per_channel, axis, eps, idx_mode):
     return _lut_tensor_launch(x, table, K, threshold, per_channel, axis, eps, idx_mode, False)[1]
 
 
-def _lut_scalar_cuda(x, table, K, divisor, threshold, round_to_input_dtype):
+def _lut_scalar_cuda(x, table, K, divisor, threshold, round_to_input_dtype, multiply=False):
+    """`multiply`: normalise with x * (float)(1.0 / divisor) -- the reference's CUDA flavour of `tensor / python_number`
+    (quantizer_utils.reference_arithmetic) -- instead of the true division x / (float)divisor."""
     _dtype_tag(x)
     xd = _dense(x)
     y = torch.empty_like(xd, dtype=torch.float32)
     if xd.numel():
-        _lut_launch(xd, y, None, 0, table, K, 1, 1, None, 0.0, True, divisor, threshold, round_to_input_dtype)
+        if multiply:
+            _lut_launch(xd, y, None, 0, table, K, 1, 1, None, 0.0, 2, float(np.float32(1.0 / divisor)), threshold, round_to_input_dtype)
+        else:
+            _lut_launch(xd, y, None, 0, table, K, 1, 1, None, 0.0, 1, divisor, threshold, round_to_input_dtype)
     return y
 
 
@@ -786,7 +792,8 @@ def _lut_tensor_cpu(x, table, K, threshold, per_channel, axis, eps):
     return _lut_host(xc, table, K, _host_array(threshold, np.float32), C, inner, eps, 0, 1.0, 1.0, 0)
 
 
-def _lut_scalar_cpu(x, table, K, divisor, threshold, round_to_input_dtype):
+def _lut_scalar_cpu(x, table, K, divisor, threshold, round_to_input_dtype, multiply=False):
+    # host tensors: the reference would run libtorch's CPU kernels, i.e. a true division, whatever `multiply` says
     return _lut_host(x, table, K, None, 1, 1, 0.0, 1, divisor, threshold, round_to_input_dtype)
 
 
@@ -859,7 +866,7 @@ def _(x, table, K, threshold, per_channel, axis, eps):
 
 
 @torch.library.register_fake("mctq::fq_lut_scalar")
-def _(x, table, K, divisor, threshold, round_to_input_dtype):
+def _(x, table, K, divisor, threshold, round_to_input_dtype, multiply=False):
     return torch.empty_like(x, dtype=torch.float32)
 
 

@@ -6,6 +6,7 @@ here: they go through the `mctq` custom operators, i.e. the fused sm_100a LUT ke
 evaluated on CPU f32 tensors with exactly the reference's sequence of f32 operations so that derived scales
 and zero points are bit-identical.
 """
+import os
 from typing import Tuple
 
 import numpy as np
@@ -37,6 +38,48 @@ def to_torch_tensor(tensor):
     raise Exception(f'Conversion of type {type(tensor)} to {type(torch.Tensor)} is not supported')
 
 
+# The reference derives its parameters with torch ops on `get_working_device()`, and ONE of those ops is not the same
+# function on the two devices: `tensor / python_number` is a true IEEE division on CPU, but libtorch's CUDA kernel
+# multiplies by the f32 reciprocal of the number (aten/native/cuda/BinaryDivTrueKernel.cu).  For `/ (2 ** n_bits - 1)`
+# (range fixing, reference :76; WeightsUniform scales, weights_uniform_inferable_quantizer.py:123) the two differ by one
+# ulp for most ranges -- and the truncated zero point then differs by one in rare cases.  So the unmodified reference
+# gives (slightly) different quantized models on a CUDA machine and on a CPU machine.  This package computes parameters
+# on the host and reproduces the CPU flavour by default (what the golden fixtures pin; the same numbers on every
+# machine); `reference_arithmetic("cuda")` reproduces, bit for bit, what the reference computes when a GPU is visible
+# (checked against the reference running on the B200: tools/differential_fuzz.py), "auto" follows the machine like the
+# reference does.  Divisions by powers of two (symmetric / POT quantizers, LUT scaling) are exact either way.  The third
+# site is in the inference path itself: ActivationLutPOT normalises with `tensor / (threshold + eps)` on every call
+# (reference :145-170 via int_quantization_with_threshold); for CUDA inputs that is x * (float)(1.0 / (thr + eps)), which
+# moves exact rounding ties between two centroids (lut_quantizer below; kernels: MCTQ_LUT_DIVISOR_IS_MULTIPLIER).
+_REFERENCE_ARITHMETIC = os.environ.get("MCTQ_REFERENCE_ARITHMETIC", "cpu")
+
+
+def reference_arithmetic(mode: str = None) -> str:
+    """Get / set the flavour of the reference's parameter arithmetic that constructors reproduce: "cpu" (default), "cuda",
+    or "auto" (cuda when a GPU is visible, like the reference itself).  Returns the previous setting.  Affects quantizers
+    constructed afterwards."""
+    global _REFERENCE_ARITHMETIC
+    prev = _REFERENCE_ARITHMETIC
+    if mode is not None:
+        if mode not in ("cpu", "cuda", "auto"):
+            raise ValueError('reference_arithmetic: mode must be "cpu", "cuda" or "auto"')
+        _REFERENCE_ARITHMETIC = mode
+    return prev
+
+
+def _cuda_flavour() -> bool:
+    mode = _REFERENCE_ARITHMETIC
+    return mode == "cuda" or (mode == "auto" and torch.cuda.is_available())
+
+
+def div_by_python_number(t: torch.Tensor, k) -> torch.Tensor:
+    """`t / k` for an f32 CPU tensor `t` and a Python number `k`, the way the reference's tensors would see it on the
+    device flavour selected by reference_arithmetic()."""
+    if _cuda_flavour():
+        return t * float(np.float32(1.0 / float(k)))           # a * (float)(1.0 / b): reciprocal in double, narrowed to f32
+    return t / k
+
+
 def fix_range_to_include_zero(range_min: torch.Tensor, range_max: torch.Tensor, n_bits: int) -> Tuple[torch.Tensor, torch.Tensor]:
     """Shift [min, max] so that 0.0 falls on the quantization grid (f32 tensor arithmetic, round-half-even).
 
@@ -49,7 +92,7 @@ def fix_range_to_include_zero(range_min: torch.Tensor, range_max: torch.Tensor, 
     straddles = torch.logical_and(torch.logical_not(lo_is_pos), torch.logical_not(hi_is_neg)).float()
     lo_is_pos, hi_is_neg = lo_is_pos.float(), hi_is_neg.float()
 
-    step = (range_max - range_min) / (2 ** n_bits - 1)
+    step = div_by_python_number(range_max - range_min, 2 ** n_bits - 1)
     lo_adj = step * torch.round(range_min / step)
     hi_adj = range_max - range_min + lo_adj
 
@@ -127,5 +170,8 @@ def lut_quantizer(tensor_data: torch.Tensor,
     # their dtype through the normalisation (the reference's eager ops round after each step)
     divisor = float(threshold) + float(eps)
     fn = ops._lut_scalar_cuda if direct else torch.ops.mctq.fq_lut_scalar
-    # round_to_input_dtype=True is a no-op for f32 inputs; passing the constant keeps the call fx-traceable
-    return fn(tensor_data, table, K, divisor, float(threshold), True)
+    # round_to_input_dtype=True is a no-op for f32 inputs; passing the constant keeps the call fx-traceable.
+    # Last argument: `tensor / python_number` on a CUDA tensor is a multiplication by the reciprocal in libtorch (see
+    # reference_arithmetic above); the CUDA implementation of the operator reproduces exactly that when asked to, the
+    # host-tensor implementation keeps the CPU kernel's true division (nothing here looks at the tensor: fx-traceable).
+    return fn(tensor_data, table, K, divisor, float(threshold), True, _cuda_flavour())

@@ -8,7 +8,7 @@ import torch
 from mct_quantizers_b200.common.base_inferable_quantizer import mark_quantizer, QuantizationTarget, QuantizerID
 from mct_quantizers_b200.common.constants import ONNX_CUSTOM_OP_DOMAIN
 from mct_quantizers_b200.common.quant_info import QuantizationMethod
-from mct_quantizers_b200.pytorch.quantizer_utils import fix_range_to_include_zero, get_working_device
+from mct_quantizers_b200.pytorch.quantizer_utils import fix_range_to_include_zero, get_working_device, div_by_python_number
 from mct_quantizers_b200.pytorch.quantizers.base_quantizer_autograd_function import _per_channel_view
 from mct_quantizers_b200.pytorch.quantizers.base_uniform_inferable_quantizer import BaseUniformInferableQuantizer
 from mct_quantizers_b200.pytorch.quantizers.weights_inferable_quantizers.base_weight_quantizer_autograd_function import \
@@ -52,7 +52,7 @@ class WeightsUniformInferableQuantizer(BaseUniformInferableQuantizer):
         # step and zero point in f32 on the host; NB the zero point is TRUNCATED toward zero (.int()), not
         # rounded -- that is what the reference does and what the golden vectors pin
         lo, hi = self.min_range.cpu(), self.max_range.cpu()
-        scales = (hi - lo) / (2 ** num_bits - 1)
+        scales = div_by_python_number(hi - lo, 2 ** num_bits - 1)     # device flavour of the reference's `/`: quantizer_utils.py
         zero_points = -(lo / scales).int()
         zp_lo, zp_hi = int(zero_points.min()), int(zero_points.max())
         if zp_lo < self.min_quantized_domain or zp_hi > self.max_quantized_domain:

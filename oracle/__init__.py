@@ -97,9 +97,10 @@ def fq_affine(x, dtype, scale, zp, C, inner, qmin, qmax, want_codes=False):
     return (y, codes) if want_codes else y
 
 
-def fq_lut(x, dtype, lut, thr, C, inner, bw, signed, eps, activation_mode=False, want_idx=False):
+def fq_lut(x, dtype, lut, thr, C, inner, bw, signed, eps, activation_mode=False, want_idx=False, cuda_flavour=False):
     """LUT fake-quant.  `thr`: f32 array [C] (weights mode) or a Python float (activation mode).
-    Returns f32 y (and int32 LUT indices)."""
+    `cuda_flavour` (activation mode): normalise with x * f32(1 / (thr + eps)) -- what the reference computes for CUDA
+    tensors -- instead of the CPU kernel's true division.  Returns f32 y (and int32 LUT indices)."""
     a = _as_raw(x, dtype)
     lut = np.ascontiguousarray(lut, dtype=np.float32).reshape(-1)
     y = np.empty(a.shape, dtype=np.float32)
@@ -114,7 +115,7 @@ def fq_lut(x, dtype, lut, thr, C, inner, bw, signed, eps, activation_mode=False,
         assert thr_arr.size == C
     rc = lib().mctq_oracle_fq_lut(_ptr(a), _ptr(y), _ptr(idx), a.size, dtype, _ptr(lut), lut.size,
                                   _ptr(thr_arr), C, inner, int(bw), int(bool(signed)), float(eps),
-                                  int(bool(activation_mode)), thr_scalar)
+                                  (2 if cuda_flavour else 1) if activation_mode else 0, thr_scalar)
     assert rc == 0
     return (y, idx) if want_idx else y
 

@@ -354,3 +354,30 @@ def test_product_never_imports_the_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", src, flags=re.M), os.path.join(dirpath, f)
+
+
+def test_reference_arithmetic_flavours():
+    """`tensor / python_number` is a true division in libtorch's CPU kernel and a multiplication by the f32 reciprocal in its
+    CUDA kernel, so the unmodified reference derives (slightly) different scales -- and now and then a different zero
+    point -- on a CUDA machine.  Known answers: the 'cuda' column was printed by the unmodified reference running on a
+    B200 (tools/differential_fuzz.py found the difference), the 'cpu' column by the same reference in the build container."""
+    cases = [  # bits, min, max, (cuda scale, cuda zp), (cpu scale, cpu zp)
+        (6, -1.4895310758373934, 4.583981513977051, (0.09640496969223022, 14), (0.09640496224164963, 15)),
+        (3, -3.3297648164422617, 10.17188549041748, (1.928807258605957, 2), (1.9288071393966675, 2)),
+        (4, -3.388154673240042, 6.393187046051025, (0.6520894765853882, 5), (0.6520894169807434, 5)),
+        (4, -2.6913525735410344, 4.400905132293701, (0.47281718254089355, 6), (0.47281715273857117, 6)),
+        (7, -1.866444401955146, 8.238741874694824, (0.07956839352846146, 23), (0.07956840097904205, 23)),
+        (3, -2.1926928017257845, 3.288418769836426, (0.7830159664154053, 3), (0.7830159068107605, 3)),
+    ]
+    assert mctq.reference_arithmetic() == "cpu"
+    try:
+        for mode, col in (("cuda", 3), ("cpu", 4)):
+            mctq.reference_arithmetic(mode)
+            for c in cases:
+                q = Q.WeightsUniformInferableQuantizer(c[0], [c[1]], [c[2]], False)
+                assert np.float32(q.scales.cpu().item()) == np.float32(c[col][0]), (mode, c)
+                assert int(q.zero_points.cpu().item()) == c[col][1], (mode, c)
+        with pytest.raises(ValueError):
+            mctq.reference_arithmetic("gpu")
+    finally:
+        mctq.reference_arithmetic("cpu")

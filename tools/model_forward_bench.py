@@ -118,6 +118,7 @@ def main():
     from mct_quantizers.pytorch import quantizers as refQ
     import mct_quantizers_b200 as b2
     from mct_quantizers_b200.pytorch import quantizers as b2Q
+    b2.reference_arithmetic("cuda")         # the reference derives its parameters on the GPU here (see quantizer_utils.py)
     assert "baseline" in ref.__file__, ref.__file__
     dev = torch.device("cuda:0")
     torch.backends.cudnn.benchmark = False

@@ -63,6 +63,7 @@ def main():
     from mct_quantizers import pytorch_quantizers as RQ
     import mct_quantizers_b200 as mctq
     from mct_quantizers_b200.pytorch import quantizers as BQ
+    mctq.reference_arithmetic("cuda")       # compare with what the reference derives on THIS machine (see quantizer_utils.py)
     for name in ("MCT Quantizers", "MCT Quantizers B200"):
         logging.getLogger(name).setLevel(logging.ERROR)
     dev = torch.device("cuda:0")
