@@ -4,7 +4,7 @@ eager LUT composition) against this package, same constructor arguments, same CU
 
     python tools/differential_fuzz.py [--cases 400] [--seed 0] [--json out.json]
 
-Random over: the nine quantizer classes; 2-8 bits (LUT: up to 16 centroids on 4-10 bit grids, sorted or shuffled, with
+Random over: the nine quantizer classes; 2-8 bits and, for the affine classes, 9-24 bits (LUT: up to 16 centroids on 4-10 bit grids, sorted or shuffled, with
 duplicates); per-tensor / per-channel on any axis of 1-4-D shapes with odd sizes; float32 / bfloat16 / float16;
 thresholds from 2^-6 to 2^4 (powers of two for the POT classes); contiguous tensors and channels_last / transposed views;
 inputs with ties planted at the rounding points, +-0, denormals, +-inf (huge values only where the zero point is 0).  The parity ORACLE stays the reference's CPU path
@@ -94,6 +94,8 @@ def main():
         dtype = dtypes[int(rng.integers(0, 3))]
         shape = rand_shape()
         bits = int(rng.integers(2, 9))
+        if "lut" not in kind and rng.random() < 0.25:
+            bits = int(rng.choice([9, 10, 12, 16, 20, 24]))      # wide grids: beyond 2^21 codes the kernels switch to the rint path
         per_channel = bool(rng.random() < 0.7) and len(shape) >= 1
         axis = int(rng.integers(0, len(shape)))
         C = shape[axis] if per_channel else 1
