@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--arithmetic", default="cuda", choices=["cpu", "cuda"],
                     help="flavour of the reference's parameter arithmetic this package reproduces (the reference itself uses the CUDA "
                          "flavour on this machine; \"cpu\" shows what the default setting differs in)")
+    ap.add_argument("--thr-exp", type=int, default=0, help="0: thresholds in 2^-6 .. 2^4; E > 0: a third of the cases draws them from 2^-E .. 2^E")
     ap.add_argument("--show", type=int, default=-1, help="print every detail of this case number")
     ap.add_argument("--dry", action="store_true", help="build container (no GPU): construct both sides, run the reference on CPU only")
     args = ap.parse_args()
@@ -61,11 +62,14 @@ def main():
         return tuple(max(d, 1) for d in dims)
 
     def rand_thr(pot):
+        if args.thr_exp and rng.random() < 0.34:
+            e = int(rng.integers(-args.thr_exp, args.thr_exp + 1))
+            return float(2.0 ** e) if pot else float(np.float32(2.0 ** e * rng.uniform(1.0, 2.0)))
         if pot:
             return float(2.0 ** int(rng.integers(-6, 5)))
         return float(np.float32(rng.uniform(2.0 ** -6, 16.0)))
 
-    def make_input(shape, dtype, span, huge=True):
+    def make_input(shape, dtype, span, huge=True, limit=None):
         n = int(np.prod(shape))
         v = rng.normal(0, span * 0.6, size=n).astype(np.float32)
         k = min(n // 3, 4096)
@@ -75,6 +79,8 @@ def main():
         specials = np.array([0.0, -0.0, 1e-40, -1e-40, span, -span] + ([np.inf, -np.inf, 3e38, -3e38] if huge else []), np.float32)
         m = min(specials.size, n)
         v[n - m:] = specials[:m]
+        if limit is not None:                 # keep |x / scale| < 2^31 and half-precision inputs finite (see below)
+            v = np.clip(v, -limit, limit)
         rng.shuffle(v)
         x = torch.from_numpy(v.reshape(shape)).to(dev).to(dtype)
         layout = "contiguous"
@@ -137,7 +143,9 @@ def main():
             qr, qb = getattr(RQ, cls)(**kw), getattr(BQ, cls)(**kw)
             # |x / scale| >= 2^31 is outside the contract (SURVEY 8a hazard 3) and libtorch's own kernels disagree there when
             # the zero point is not 0: the CUDA per-channel kernel wraps in int32, the CPU kernel saturates
-            x, layout = make_input(shape, dtype, float(np.mean(thr)), huge=kind not in ("w_uni", "a_uni"))
+            uni = kind in ("w_uni", "a_uni")
+            limit = min(2.0 ** 30 * min(thr) / 2.0 ** bits, 60000.0 if dtype == torch.float16 else 3e38) if uni else None
+            x, layout = make_input(shape, dtype, float(np.mean(thr)), huge=not uni, limit=limit)
             if kind.startswith("w_") and not x.is_contiguous() and per_channel:
                 x = x.contiguous()                      # the reference's weight path is only ever fed contiguous parameters
                 layout = "contiguous"
