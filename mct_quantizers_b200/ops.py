@@ -561,11 +561,11 @@ def _lut_tensor_launch(x, table, K, threshold, per_channel, axis, eps, idx_mode,
         if threshold.numel() != x.shape[axis]:
             raise RuntimeError(f"shape '{[1] * x.dim()}' is invalid for threshold of size {threshold.numel()} "
                                f"(input has {x.shape[axis]} channels on axis {axis})")
-        xd, C, inner = _channel_layout(x, axis)
+        xd, C, inner = _channel_layout(x.contiguous(), axis)     # row-major output like the reference's eager composition
     else:
         if threshold.numel() != 1:
             raise RuntimeError("per-tensor LUT quantization needs a single threshold")
-        xd, C, inner = _dense(x), 1, 1
+        xd, C, inner = x.contiguous(), 1, 1
     n = xd.numel()
     y = torch.empty_like(xd, dtype=torch.float32) if want_values else None
     idx = None
@@ -636,7 +636,7 @@ def _lut_scalar_cuda(x, table, K, divisor, threshold, round_to_input_dtype, mult
     """`multiply`: normalise with x * (float)(1.0 / divisor) -- the reference's CUDA flavour of `tensor / python_number`
     (quantizer_utils.reference_arithmetic) -- instead of the true division x / (float)divisor."""
     _dtype_tag(x)
-    xd = _dense(x)
+    xd = x.contiguous()        # the reference's eager composition (argmin + gather) returns a row-major tensor whatever x's strides
     y = torch.empty_like(xd, dtype=torch.float32)
     if xd.numel():
         if multiply:
