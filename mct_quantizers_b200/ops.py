@@ -576,6 +576,8 @@ def _lut_tensor_launch(x, table, K, threshold, per_channel, axis, eps, idx_mode,
     if n:
         thr = _param_on(threshold.contiguous(), xd.device)
         _lut_launch(xd, y, idx, idx_mode, table, K, C, inner, thr, eps, False, 1.0, 1.0, False)
+    if y is not None and y.dim() == 0:
+        y = y.reshape(1)        # the reference multiplies by the threshold TENSOR of shape (1,): a 0-dim input comes back 1-D
     return y, idx
 
 
@@ -584,7 +586,7 @@ def lut_weights_direct(x, table, K, threshold, per_channel, axis, eps, cache):
     building: ~35 us -> ~10 us of host time per call, which matters once a 45 M-element bf16 matrix takes 40 us on the
     device).  `cache` is a dict owned by the quantizer: (shape, dtype, device, thr ptr) -> launch constants.  Anything
     unusual (non-contiguous input, no prepared blob, misaligned view) goes through the general path."""
-    if x.is_contiguous() and x.numel():
+    if x.is_contiguous() and x.numel() and x.dim():        # (0-dim inputs: general path, which returns them 1-D like the reference)
         key = (x.shape, x.dtype, x.device, threshold.data_ptr(), _ver(threshold))
         hit = cache.get(key)
         if hit is None:

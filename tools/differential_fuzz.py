@@ -55,6 +55,11 @@ def main():
     dtypes = [torch.float32, torch.bfloat16, torch.float16]
 
     def rand_shape():
+        r = rng.random()
+        if r < 0.03:
+            return ()                                   # 0-dim tensor
+        if r < 0.06:
+            return (0, int(rng.integers(1, 9)))         # empty tensor
         nd = int(rng.integers(1, 5))
         dims = [int(rng.choice([1, 2, 3, 5, 7, 8, 9, 16, 17, 31, 32, 33, 64, 100, 129])) for _ in range(nd)]
         while int(np.prod(dims)) > 600000:
@@ -70,7 +75,7 @@ def main():
         return float(np.float32(rng.uniform(2.0 ** -6, 16.0)))
 
     def make_input(shape, dtype, span, huge=True, limit=None):
-        n = int(np.prod(shape))
+        n = int(np.prod(shape)) if len(shape) else 1
         v = rng.normal(0, span * 0.6, size=n).astype(np.float32)
         k = min(n // 3, 4096)
         if k:
@@ -78,7 +83,8 @@ def main():
             v[:k] = grid * np.float32(span / 128.0) * np.float32(rng.choice([1.0, 0.5, 2.0]))
         specials = np.array([0.0, -0.0, 1e-40, -1e-40, span, -span] + ([np.inf, -np.inf, 3e38, -3e38] if huge else []), np.float32)
         m = min(specials.size, n)
-        v[n - m:] = specials[:m]
+        if m:
+            v[n - m:] = specials[:m]
         if limit is not None:                 # keep |x / scale| < 2^31 and half-precision inputs finite (see below)
             v = np.clip(v, -limit, limit)
         rng.shuffle(v)
@@ -103,8 +109,9 @@ def main():
         bits = int(rng.integers(2, 9))
         if "lut" not in kind and rng.random() < 0.25:
             bits = int(rng.choice([9, 10, 12, 16, 20, 24]))      # wide grids: beyond 2^21 codes the kernels switch to the rint path
-        per_channel = bool(rng.random() < 0.7) and len(shape) >= 1
-        axis = int(rng.integers(0, len(shape)))
+        degenerate = len(shape) == 0 or 0 in shape
+        per_channel = bool(rng.random() < 0.7) and not degenerate
+        axis = int(rng.integers(0, len(shape))) if not degenerate else 0
         C = shape[axis] if per_channel else 1
         pot = kind in ("w_pot", "w_lut_pot", "a_pot", "a_lut")
         thr = [rand_thr(pot) for _ in range(C)]
