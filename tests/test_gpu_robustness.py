@@ -395,3 +395,28 @@ def test_nvtx_ranges_can_be_switched_on():
         assert torch.equal(q(x), want)
     finally:
         assert lib.mctq_set_tuning(9, prev) == 1
+
+
+def test_lut_outputs_follow_the_reference_in_shape_and_strides(Q):
+    """Two things the differential fuzzer (tools/differential_fuzz.py, against the unmodified reference on the B200) found:
+    the reference's eager LUT composition (argmin + gather) returns a ROW-MAJOR tensor whatever the input's strides (the
+    affine quantizers keep the input's strides, like ATen), and a 0-dim input of a per-tensor LUT weights quantizer comes
+    back 1-D because the result is multiplied by the threshold tensor of shape (1,)."""
+    lut = [-8.0, -3.0, 0.0, 2.0, 7.0]
+    x = torch.randn(4, 6, 5, 3, device=DEV).contiguous(memory_format=torch.channels_last)
+    qa = Q.ActivationLutPOTInferableQuantizer(4, lut, [2.0], True, 4)
+    ya = qa(x)
+    assert ya.is_contiguous() and torch.equal(ya, qa(x.contiguous()))
+    qw = Q.WeightsLUTSymmetricInferableQuantizer(4, lut, [1.5], False, None, None, 4)
+    yw = qw(x.clone())
+    assert yw.is_contiguous() and torch.equal(yw, qw(x.contiguous()))
+    xt = torch.randn(7, 12, device=DEV).t()
+    qc = Q.WeightsLUTSymmetricInferableQuantizer(4, lut, [1.0 + 0.1 * k for k in range(12)], True, 0, 2, 4)
+    yc = qc(xt.clone())
+    assert yc.is_contiguous() and torch.equal(yc, qc(xt.contiguous()))
+    # affine: strides preserved
+    qs = Q.ActivationSymmetricInferableQuantizer(8, [4.0], True)
+    assert qs(x).stride() == x.stride()
+    # 0-dim
+    s = torch.tensor(0.7, device=DEV)
+    assert qw(s.clone()).shape == (1,) and qa(s).shape == () and qs(s).shape == ()
