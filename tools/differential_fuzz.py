@@ -38,6 +38,7 @@ def main():
                     help="flavour of the reference's parameter arithmetic this package reproduces (the reference itself uses the CUDA "
                          "flavour on this machine; \"cpu\" shows what the default setting differs in)")
     ap.add_argument("--thr-exp", type=int, default=0, help="0: thresholds in 2^-6 .. 2^4; E > 0: a third of the cases draws them from 2^-E .. 2^E")
+    ap.add_argument("--export", action="store_true", help="compare the ONNX-export branch instead: enable_custom_impl() + torch.jit.trace on both sides")
     ap.add_argument("--show", type=int, default=-1, help="print every detail of this case number")
     ap.add_argument("--dry", action="store_true", help="build container (no GPU): construct both sides, run the reference on CPU only")
     args = ap.parse_args()
@@ -155,8 +156,14 @@ def main():
             limit = min(2.0 ** 30 * min(thr) / 2.0 ** bits, 60000.0 if dtype == torch.float16 else 3e38) if uni else None
             x, layout = make_input(shape, dtype, float(np.mean(thr)), huge=not uni, limit=limit)
             with torch.no_grad():
-                yr = qr(x.clone())
-                yb = yr if args.dry else qb(x.clone())
+                if args.export:
+                    qr.enable_custom_impl()
+                    qb.enable_custom_impl()
+                    yr = torch.jit.trace(lambda t: qr(t), x.clone(), check_trace=False)(x.clone())
+                    yb = yr if args.dry else torch.jit.trace(lambda t: qb(t), x.clone(), check_trace=False)(x.clone())
+                else:
+                    yr = qr(x.clone())
+                    yb = yr if args.dry else qb(x.clone())
             assert yr.dtype == yb.dtype and yr.shape == yb.shape, (yr.dtype, yb.dtype, yr.shape, yb.shape)
             if yr.stride() != yb.stride() and yr.numel() > 1 and all(d > 1 for d in yr.shape):
                 strides_differ.append({"case": it, "kind": kind, "shape": list(shape), "layout": layout, "reference": list(yr.stride()), "b200": list(yb.stride())})
