@@ -38,6 +38,8 @@ def main():
                     help="flavour of the reference's parameter arithmetic this package reproduces (the reference itself uses the CUDA "
                          "flavour on this machine; \"cpu\" shows what the default setting differs in)")
     ap.add_argument("--thr-exp", type=int, default=0, help="0: thresholds in 2^-6 .. 2^4; E > 0: a third of the cases draws them from 2^-E .. 2^E")
+    ap.add_argument("--oracle", action="store_true", help="build container (no GPU): the reference on CPU against the C oracle + the oracle's "
+                    "restatement of the constructor math (oracle/, tests/golden_util.py) -- widens the pinning of the oracle beyond the fixtures")
     ap.add_argument("--export", action="store_true", help="compare the ONNX-export branch instead: enable_custom_impl() + torch.jit.trace on both sides")
     ap.add_argument("--show", type=int, default=-1, help="print every detail of this case number")
     ap.add_argument("--dry", action="store_true", help="build container (no GPU): construct both sides, run the reference on CPU only")
@@ -51,6 +53,11 @@ def main():
     import mct_quantizers_b200
     from mct_quantizers_b200.pytorch import quantizers as BQ
     mct_quantizers_b200.reference_arithmetic(args.arithmetic)
+    if args.oracle:
+        args.dry = True
+        args.arithmetic = "cpu"
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import golden_util as G
     dev = torch.device("cpu" if args.dry else "cuda:0")
     rng = np.random.default_rng(args.seed)
     dtypes = [torch.float32, torch.bfloat16, torch.float16]
@@ -154,13 +161,21 @@ def main():
             # the zero point is not 0: the CUDA per-channel kernel wraps in int32, the CPU kernel saturates
             uni = kind in ("w_uni", "a_uni")
             limit = min(2.0 ** 30 * min(thr) / 2.0 ** bits, 60000.0 if dtype == torch.float16 else 3e38) if uni else None
-            x, layout = make_input(shape, dtype, float(np.mean(thr)), huge=not uni, limit=limit)
+            # (--oracle: libtorch's CPU per-channel kernel converts through int64 and turns +inf / 3e38 into quant_min, its
+            # per-tensor kernel saturates; outside the contract either way, the oracle saturates)
+            huge = not uni and not (args.oracle and per_channel and kind in ("w_sym", "w_pot"))
+            x, layout = make_input(shape, dtype, float(np.mean(thr)), huge=huge, limit=limit)
             with torch.no_grad():
                 if args.export:
                     qr.enable_custom_impl()
                     qb.enable_custom_impl()
                     yr = torch.jit.trace(lambda t: qr(t), x.clone(), check_trace=False)(x.clone())
                     yb = yr if args.dry else torch.jit.trace(lambda t: qb(t), x.clone(), check_trace=False)(x.clone())
+                elif args.oracle:
+                    yr = qr(x.clone()).contiguous()
+                    case = {"cls": cls, "args": dict(kw), "shape": list(x.shape), "x_dtype": str(dtype).replace("torch.", "")}
+                    got = np.asarray(G.oracle_run(case, G.from_torch(x))["y"]).reshape(yr.shape)
+                    yb = G.to_torch(np.ascontiguousarray(got), str(yr.dtype).replace("torch.", "")).reshape(yr.shape)
                 else:
                     yr = qr(x.clone())
                     yb = yr if args.dry else qb(x.clone())
