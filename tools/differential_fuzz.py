@@ -41,6 +41,7 @@ def main():
     ap.add_argument("--oracle", action="store_true", help="build container (no GPU): the reference on CPU against the C oracle + the oracle's "
                     "restatement of the constructor math (oracle/, tests/golden_util.py) -- widens the pinning of the oracle beyond the fixtures")
     ap.add_argument("--export", action="store_true", help="compare the ONNX-export branch instead: enable_custom_impl() + torch.jit.trace on both sides")
+    ap.add_argument("--cpu", action="store_true", help="with --export: run both sides on CPU tensors (the export formulas are plain torch ops; works without a GPU)")
     ap.add_argument("--show", type=int, default=-1, help="print every detail of this case number")
     ap.add_argument("--dry", action="store_true", help="build container (no GPU): construct both sides, run the reference on CPU only")
     args = ap.parse_args()
@@ -58,7 +59,11 @@ def main():
         args.arithmetic = "cpu"
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import golden_util as G
-    dev = torch.device("cpu" if args.dry else "cuda:0")
+    if args.cpu:
+        assert args.export, "--cpu only makes sense for the export branch (the inference path has no CPU arithmetic)"
+        args.arithmetic = "cpu"
+        mct_quantizers_b200.reference_arithmetic("cpu")
+    dev = torch.device("cpu" if (args.dry or args.cpu) else "cuda:0")
     rng = np.random.default_rng(args.seed)
     dtypes = [torch.float32, torch.bfloat16, torch.float16]
 
