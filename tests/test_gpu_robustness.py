@@ -420,3 +420,44 @@ def test_lut_outputs_follow_the_reference_in_shape_and_strides(Q):
     # 0-dim
     s = torch.tensor(0.7, device=DEV)
     assert qw(s.clone()).shape == (1,) and qa(s).shape == () and qs(s).shape == ()
+
+
+def test_concurrent_threads_on_their_own_streams(Q):
+    """Four Python threads, each on its own CUDA stream, hammer the same quantizer objects (ctypes releases the GIL inside
+    the native calls, so launches, the per-stream dependent-launch bookkeeping and the prepared-parameter caches really
+    run concurrently): every result equals the single-threaded one."""
+    import threading
+    rng = np.random.default_rng(77)
+    w = torch.from_numpy(rng.standard_normal((48, 1024)).astype(np.float32)).to(DEV)
+    x = torch.from_numpy(rng.standard_normal((8, 3, 64, 64)).astype(np.float32)).to(DEV)
+    thr = [float(v) for v in w.abs().amax(1)]
+    qs = [Q.WeightsSymmetricInferableQuantizer(8, thr, True, 0),
+          Q.WeightsLUTSymmetricInferableQuantizer(4, [-100.0, -30.0, -8.0, 0.0, 5.0, 21.0, 77.0, 127.0], thr, True, 0, 2),
+          Q.ActivationUniformInferableQuantizer(8, [-1.0], [2.5]),
+          Q.ActivationLutPOTInferableQuantizer(4, [-8.0, -3.0, 0.0, 2.0, 7.0], [2.0], True, 4)]
+    ins = [w, w, x, x]
+    want = [q(t.clone()) for q, t in zip(qs, ins)]
+    torch.cuda.synchronize()
+    errors = []
+
+    def work(k):
+        try:
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                for it in range(150):
+                    j = (it + k) % len(qs)
+                    y = qs[j](ins[j])
+                    if it % 10 == 0:
+                        st.synchronize()
+                        if not torch.equal(y, want[j]):
+                            errors.append((k, it, j))
+            st.synchronize()
+        except Exception as e:          # noqa: BLE001
+            errors.append((k, repr(e)))
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:5]
